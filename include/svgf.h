@@ -1,0 +1,191 @@
+/*
+ * svgf.h — C ABI of the B200-native SVGF filter (libsvgf_b200.so).
+ *
+ * Drop-in boundary for the one hot path of jacquespillet/SVGF: the three private stage methods of
+ * `application` that launch the Filter.cuh kernels (reference src/App.cu:469-514, called in order from
+ * Render() src/App.cu:552-556, ping-pong flip in EndFrame() src/App.cu:366-375).  Every entry point below
+ * names the reference call site / kernel it replaces.
+ *
+ * Conventions
+ *  - All image pointers are caller-owned DEVICE memory, row-major, dense (`y*W + x`) for the colour /
+ *    moments / history planes exactly like the reference's `buffer`s (src/App.cu:763-773); G-buffer planes
+ *    carry a row pitch in bytes (0 = dense) because they originate from GL attachments.
+ *  - Texel formats are the reference's (src/App.cu:746-752, resources/shaders/GBuffer.frag:62-87):
+ *      position_id  : float4  world xyz, w = primitive index            (never read by the filter; may be NULL)
+ *      normal_mat   : ushort4 fp16 bit patterns: unit normal xyz, w = material index
+ *      uv_inst      : ushort4 fp16 bit patterns: barycentrics xyz, w = instance index ("mesh id")
+ *      motion_depth : float4  xy = motion in pixels (cur -> prev), z = linear depth (0 = background),
+ *                             w = max(|dFdx z|, |dFdy z|)
+ *    colour planes  : half4 (SVGF_STORE_F16, reference layout, src/Filter.cuh:15) or float4 (SVGF_STORE_F32)
+ *                     = (r, g, b, variance);  moments planes: half2 / float2 = (E[L], E[L^2]);
+ *    history        : uint8 per pixel (src/App.cu:773).
+ *  - Calls are asynchronous on the caller's stream (a `cudaStream_t` passed as void*; NULL = default
+ *    stream); nothing synchronises the host.  Errors are returned, never asserted
+ *    (the reference asserts, src/App.cu:41-48).
+ *  - One context per (device, resolution, storage); a context is not thread-safe, different contexts are.
+ *  - There is no CPU fallback: every entry point launches sm_100a kernels or fails.
+ */
+#ifndef SVGF_B200_H
+#define SVGF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVGF_ABI_VERSION 1
+
+typedef struct svgf_ctx svgf_ctx;
+
+typedef enum svgf_status {
+    SVGF_OK = 0,
+    SVGF_INVALID_ARG = 1,
+    SVGF_UNSUPPORTED = 2,
+    SVGF_CUDA_ERROR = 3
+} svgf_status;
+
+/* Storage of colour+variance / moments planes.  F16 is the reference layout (src/Filter.cuh:15-16). */
+typedef enum svgf_storage { SVGF_STORE_F16 = 0, SVGF_STORE_F32 = 1 } svgf_storage;
+
+/* Mesh-id consistency test of the reprojection (src/Filter.cuh:245-247).
+ * INTENDED decodes uv_inst.w (fp16) to an int instance index as GBuffer.frag:77 wrote it;
+ * REFERENCE_VACUOUS reproduces what the reference's type-punned float4 fetch does on hardware
+ * (both ids read as denormals -> 0 -> the test always passes). */
+typedef enum svgf_mesh_id_mode { SVGF_MESH_ID_INTENDED = 0, SVGF_MESH_ID_REFERENCE_VACUOUS = 1 } svgf_mesh_id_mode;
+
+/* History fetch.  NEAREST_TRUNC is what the reference does (src/Filter.cuh:231-232). */
+typedef enum svgf_reproj_mode { SVGF_REPROJ_NEAREST_TRUNC = 0 } svgf_reproj_mode;
+
+/* Variance pre-filter of the a-trous levels.  NONE is what the reference does (src/Filter.cuh:547,562). */
+typedef enum svgf_variance_prefilter { SVGF_VARIANCE_PREFILTER_NONE = 0 } svgf_variance_prefilter;
+
+/* svgf_params.flags */
+#define SVGF_FLAG_NONE 0u
+/* svgf_frame only: do not reuse the compact guide plane cached from the previous svgf_frame call for the
+ * previous-frame consistency tests; always re-read prev_gbuf. */
+#define SVGF_FLAG_NO_GUIDE_CACHE 1u
+/* svgf_frame / svgf_atrous: run every a-trous level as its own launch (disables two-level fusion). */
+#define SVGF_FLAG_NO_LEVEL_FUSION 2u
+
+/* Tunables.  Defaults (svgf_default_params) are the reference's members src/App.h:109-114, GUI ranges
+ * src/GUI.cpp:988-993.  phi_depth / alpha_min / moments_alpha_min are additions whose defaults
+ * reproduce the reference exactly. */
+typedef struct svgf_params {
+    int32_t history_cap;         /* HistoryLength      = 24   (1..255; stored into uint8, src/Filter.cuh:400) */
+    float depth_threshold;       /* DepthThreshold     = 0.8  absolute, world units (src/Filter.cuh:242) */
+    float normal_threshold;      /* NormalThreshold    = 0.9  (src/Filter.cuh:252) */
+    float phi_colour;            /* PhiColour          = 10   (src/Filter.cuh:460,562) */
+    float phi_normal;            /* PhiNormal          = 128  (src/Filter.cuh:419) */
+    int32_t atrous_iterations;   /* SpatialFilterSteps = 3 in the reference; 5 in BASELINE (0..10) */
+    float phi_depth;             /* multiplies both depth phis (src/Filter.cuh:461,563); 1 = reference */
+    float alpha_min;             /* colour alpha  = max(1/h, alpha_min);          0 = reference (src/Filter.cuh:381) */
+    float moments_alpha_min;     /* moments alpha = max(1/h, moments_alpha_min);  0 = reference */
+    int32_t mesh_id_mode;        /* svgf_mesh_id_mode */
+    int32_t reproj_mode;         /* svgf_reproj_mode */
+    int32_t variance_prefilter;  /* svgf_variance_prefilter */
+    uint32_t flags;              /* SVGF_FLAG_* */
+} svgf_params;
+
+/* One G-buffer = the reference's `cudaFramebuffer` (src/App.h:41-44; attachment order src/App.h:33-39),
+ * as pitch-linear device memory instead of cudaArray texture objects (TMA needs linear memory). */
+typedef struct svgf_gbuffer {
+    const void *position_id;  size_t position_pitch;   /* float4;  may be NULL (not read by any filter kernel) */
+    const void *normal_mat;   size_t normal_pitch;     /* ushort4 (fp16 bits) */
+    const void *uv_inst;      size_t uv_pitch;         /* ushort4 (fp16 bits) */
+    const void *motion_depth; size_t motion_pitch;     /* float4 */
+} svgf_gbuffer;
+
+/* The reference's ping-pong buffer set (src/App.h:136-139) for svgf_frame. */
+typedef struct svgf_frame_buffers {
+    void *render[2];     /* RenderBuffer[0..1]  colour planes; [ping_pong] holds this frame's noisy radiance on entry */
+    void *moments[2];    /* MomentsBuffer[0..1] */
+    void *filter[2];     /* FilterBuffer[0..1]; the result lands in filter[0], filter[1] is scratch */
+    uint8_t *history;    /* HistoryLengthBuffer */
+    int32_t ping_pong;   /* PingPongInx: index of the CURRENT frame's render/moments/G-buffer */
+} svgf_frame_buffers;
+
+/* ABI version of the loaded library (== SVGF_ABI_VERSION it was built with). */
+int svgf_abi_version(void);
+const char *svgf_status_string(svgf_status s);
+
+/* Reference defaults: src/App.h:109-114 with atrous_iterations = 5 (BASELINE.json) and the added knobs neutral. */
+void svgf_default_params(svgf_params *p);
+
+/* Replaces application::ResizeRenderTextures()'s filter part (src/App.cu:742-778): the context owns only
+ * scratch — the history shadow plane (race-free snapshot semantics for src/Filter.cuh:255 vs :400), two
+ * compact guide planes and TMA descriptors.  `device` is a CUDA ordinal. */
+svgf_status svgf_create(svgf_ctx **out, int device, int width, int height, svgf_storage storage);
+void svgf_destroy(svgf_ctx *ctx);
+
+/* First-frame semantics, undefined in the reference (raw cudaMalloc, src/Buffer.cpp:20): zero-fills both
+ * render/moments planes, the history plane and the context's cached previous-frame guide, so that every
+ * pixel of the next frame fails reprojection (h = 1, alpha = 1). */
+svgf_status svgf_reset(svgf_ctx *ctx, const svgf_frame_buffers *bufs, void *stream);
+
+/* Replaces application::TemporalFilter() (src/App.cu:469-478) -> filter::TemporalFilter (src/Filter.cuh:359-404).
+ * cur_colour is updated in place to (accumulated rgb, variance); history is updated in place but with
+ * snapshot semantics (reads see the previous frame's values). */
+svgf_status svgf_temporal(svgf_ctx *ctx, const svgf_params *params,
+                          const svgf_gbuffer *cur_gbuf, const svgf_gbuffer *prev_gbuf,
+                          const void *prev_colour, void *cur_colour, uint8_t *history,
+                          void *cur_moments, const void *prev_moments, void *stream);
+
+/* Replaces application::FilterMoments() (src/App.cu:480-489) -> filter::FilterMoments (src/Filter.cuh:430-525).
+ * `moments` is explicit: the reference always passes MomentsBuffer[0] (src/App.cu:484). */
+svgf_status svgf_variance(svgf_ctx *ctx, const svgf_params *params, const svgf_gbuffer *cur_gbuf,
+                          const void *colour_in, const void *moments, const uint8_t *history,
+                          void *colour_out, void *stream);
+
+/* Replaces application::WaveletFilter()'s loop body (src/App.cu:497-508) -> filter::FilterKernel
+ * (src/Filter.cuh:527-624) for levels first_level .. first_level+num_levels-1 (Step = 1 << level).
+ * Ping-pongs between buf_a (input of first_level) and buf_b; the final level's output pointer is returned in
+ * *result (either buf_a or buf_b).  history_colour_out receives the level-0 output (non-background
+ * pixels only, src/Filter.cuh:554-558,619-622) when level 0 is among the levels run; may be NULL otherwise. */
+svgf_status svgf_atrous(svgf_ctx *ctx, const svgf_params *params, const svgf_gbuffer *cur_gbuf,
+                        void *buf_a, void *buf_b, void *history_colour_out,
+                        int first_level, int num_levels, void **result, void *stream);
+
+/* Replaces the stage sequence of application::Render() (src/App.cu:552-556): temporal -> variance ->
+ * atrous_iterations levels.  gbuf[ping_pong] is the current G-buffer, gbuf[1-ping_pong] the previous.
+ * After the call: filter[0] = final result; render[ping_pong] = next frame's colour history (level-0 output;
+ * temporal output for background pixels or when atrous_iterations == 0); moments[ping_pong], history
+ * updated.  Stages may be fused internally; the buffers named here match the unfused sequence.
+ * The caller flips ping_pong afterwards (EndFrame, src/App.cu:374). */
+svgf_status svgf_frame(svgf_ctx *ctx, const svgf_params *params, const svgf_gbuffer gbuf[2],
+                       const svgf_frame_buffers *bufs, void *stream);
+
+/* The context caches a compact "guide" plane (depth, depth derivative, normal, mesh id: 16 B/px) per
+ * G-buffer, keyed by the motion_depth pointer: svgf_temporal / svgf_frame build it for the current
+ * G-buffer, the following svgf_variance / svgf_atrous calls naming the same G-buffer reuse it, and the next
+ * frame's temporal pass reads it as the previous-frame guide (the reference's two ping-ponged framebuffers,
+ * src/App.cu:745-746, satisfy this by construction).  Call this after modifying a G-buffer in place outside
+ * that order; svgf_reset implies it. */
+void svgf_invalidate_guide(svgf_ctx *ctx);
+
+/* Stage timing for benchmarks: between begin and end every svgf_frame records four CUDA events on the
+ * caller's stream (before temporal / variance / a-trous, after a-trous; up to 4096 frames).  end
+ * synchronises the last event and returns summed GPU milliseconds per stage {temporal, variance, atrous}. */
+svgf_status svgf_profile_begin(svgf_ctx *ctx);
+svgf_status svgf_profile_end(svgf_ctx *ctx, double stage_ms[3], int *frames);
+
+/* Last CUDA error code seen by this context (cudaError_t as int), 0 if none. */
+int svgf_last_cuda_error(const svgf_ctx *ctx);
+
+/* Number of kernel launches issued through this context so far (for bench accounting). */
+uint64_t svgf_launch_count(const svgf_ctx *ctx);
+
+/* Host-buffer convenience used by the end-to-end benchmark and by callers without device memory of their
+ * own: copies one frame's inputs host->device, runs svgf_frame, copies the result device->host.
+ * `h_*` are pinned or pageable HOST pointers in the same texel formats; the previous frame's state stays
+ * resident in the context between calls (reset=1 starts a new sequence). */
+svgf_status svgf_frame_host(svgf_ctx *ctx, const svgf_params *params,
+                            const void *h_normal_mat, const void *h_uv_inst, const void *h_motion_depth,
+                            const void *h_noisy_colour, void *h_result, uint8_t *h_history_out,
+                            int reset, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVGF_B200_H */

@@ -1,0 +1,489 @@
+// svgf_api.cu — the C ABI of include/svgf.h over the sm_100a kernels.  Host side only: argument validation,
+// context-owned scratch (history shadow plane, compact guide planes), stage sequencing and buffer rotation.
+// There is no CPU implementation of any stage in this library.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/svgf.h"
+#include "svgf_kernels_basic.cuh"
+
+using namespace svgf;
+
+struct svgf_ctx {
+    int device = 0, W = 0, H = 0;
+    svgf_storage storage = SVGF_STORE_F16;
+    uint8_t *hist_shadow = nullptr;       // this frame's history lengths until published (D3)
+    float4 *guide[2] = {nullptr, nullptr};  // compact guide planes, ping-pong
+    const void *guide_key[2] = {nullptr, nullptr};  // motion_depth pointer of the G-buffer each plane was built from
+    int guide_cur = 0;                    // slot of the most recently built guide
+    bool force_fail_next = false;         // set by svgf_reset
+    int last_err = 0;
+    uint64_t launches = 0;
+    // stage profiling (svgf_profile_*): events around temporal / variance / a-trous inside svgf_frame
+    bool profiling = false;
+    static constexpr int kMaxProf = 4096;
+    cudaEvent_t *prof_ev = nullptr;       // 4 events per frame
+    int prof_frames = 0;
+    // device-resident state of the host-buffer path (svgf_frame_host)
+    struct HostPath {
+        void *normal[2] = {nullptr, nullptr}, *uv[2] = {nullptr, nullptr}, *motion[2] = {nullptr, nullptr};
+        void *render[2] = {nullptr, nullptr}, *moments[2] = {nullptr, nullptr}, *filter[2] = {nullptr, nullptr};
+        uint8_t *history = nullptr;
+        int ping_pong = 0;
+        bool ready = false;
+    } hp;
+};
+
+namespace {
+
+inline size_t colour_bytes(const svgf_ctx *c) { return (size_t)c->W * c->H * (c->storage == SVGF_STORE_F32 ? 16 : 8); }
+inline size_t moments_bytes(const svgf_ctx *c) { return (size_t)c->W * c->H * (c->storage == SVGF_STORE_F32 ? 8 : 4); }
+
+svgf_status cuda_fail(svgf_ctx *c, cudaError_t e) {
+    if (c) c->last_err = (int)e;
+    return SVGF_CUDA_ERROR;
+}
+#define SVGF_CUDA(c, x)                                    \
+    do {                                                   \
+        cudaError_t e_ = (x);                              \
+        if (e_ != cudaSuccess) return cuda_fail((c), e_);  \
+    } while (0)
+
+svgf_status check_params(const svgf_params *p) {
+    if (!p) return SVGF_INVALID_ARG;
+    if (p->history_cap < 1 || p->history_cap > 255) return SVGF_INVALID_ARG;  // D9: stored into uint8
+    if (p->atrous_iterations < 0 || p->atrous_iterations > 10) return SVGF_INVALID_ARG;
+    if (!(p->phi_colour > 0.0f) || !(p->phi_normal >= 0.0f) || !(p->phi_depth >= 0.0f)) return SVGF_INVALID_ARG;
+    if (!(p->depth_threshold >= 0.0f)) return SVGF_INVALID_ARG;
+    if (!(p->alpha_min >= 0.0f && p->alpha_min <= 1.0f) || !(p->moments_alpha_min >= 0.0f && p->moments_alpha_min <= 1.0f))
+        return SVGF_INVALID_ARG;
+    if (p->mesh_id_mode != SVGF_MESH_ID_INTENDED && p->mesh_id_mode != SVGF_MESH_ID_REFERENCE_VACUOUS) return SVGF_INVALID_ARG;
+    if (p->reproj_mode != SVGF_REPROJ_NEAREST_TRUNC) return SVGF_UNSUPPORTED;
+    if (p->variance_prefilter != SVGF_VARIANCE_PREFILTER_NONE) return SVGF_UNSUPPORTED;
+    if (p->phi_normal > 0.0f && p->phi_normal < 1.0f) return SVGF_UNSUPPORTED;  // see edge_weight_log2
+    return SVGF_OK;
+}
+
+svgf_status check_gbuf(const svgf_ctx *c, const svgf_gbuffer *g) {
+    if (!g || !g->normal_mat || !g->uv_inst || !g->motion_depth) return SVGF_INVALID_ARG;
+    const size_t W = (size_t)c->W;
+    if (g->normal_pitch && (g->normal_pitch < W * 8 || g->normal_pitch % 8)) return SVGF_INVALID_ARG;
+    if (g->uv_pitch && (g->uv_pitch < W * 8 || g->uv_pitch % 8)) return SVGF_INVALID_ARG;
+    if (g->motion_pitch && (g->motion_pitch < W * 16 || g->motion_pitch % 16)) return SVGF_INVALID_ARG;
+    if (((uintptr_t)g->normal_mat % 8) || ((uintptr_t)g->uv_inst % 8) || ((uintptr_t)g->motion_depth % 16)) return SVGF_INVALID_ARG;
+    return SVGF_OK;
+}
+
+GBufView view(const svgf_ctx *c, const svgf_gbuffer *g) {
+    GBufView v;
+    v.normal = (const char *)g->normal_mat;
+    v.uv = (const char *)g->uv_inst;
+    v.motion = (const char *)g->motion_depth;
+    v.normal_pitch = g->normal_pitch ? g->normal_pitch : (size_t)c->W * 8;
+    v.uv_pitch = g->uv_pitch ? g->uv_pitch : (size_t)c->W * 8;
+    v.motion_pitch = g->motion_pitch ? g->motion_pitch : (size_t)c->W * 16;
+    return v;
+}
+
+inline dim3 grid_for(const svgf_ctx *c) { return dim3((c->W + 31) / 32, (c->H + 7) / 8); }
+
+struct DeviceGuard {  // make the context's device current for the duration of a call
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Make sure a compact guide plane for `g` exists; returns its slot.
+svgf_status ensure_guide(svgf_ctx *c, const svgf_gbuffer *g, cudaStream_t s, int *slot) {
+    for (int k = 0; k < 2; k++)
+        if (c->guide_key[k] == g->motion_depth) { *slot = k; return SVGF_OK; }
+    const int k = 1 - c->guide_cur;
+    build_guide_kernel<<<grid_for(c), 256, 0, s>>>(view(c, g), c->guide[k], c->W, c->H);
+    c->launches++;
+    SVGF_CUDA(c, cudaGetLastError());
+    c->guide_key[k] = g->motion_depth;
+    c->guide_cur = k;
+    *slot = k;
+    return SVGF_OK;
+}
+
+template <bool F32>
+svgf_status launch_temporal(svgf_ctx *c, const svgf_params *p, const svgf_gbuffer *cur, const svgf_gbuffer *prev,
+                            const void *prev_colour, void *cur_colour, const uint8_t *hist_prev, uint8_t *hist_out,
+                            void *cur_mom, const void *prev_mom, cudaStream_t s) {
+    using CT = typename ColourPlane<F32>::texel;
+    using MT = typename MomentsPlane<F32>::texel;
+    TemporalArgs a;
+    a.W = c->W; a.H = c->H;
+    a.depth_threshold = p->depth_threshold; a.normal_threshold = p->normal_threshold;
+    a.history_cap = p->history_cap; a.alpha_min = p->alpha_min; a.moments_alpha_min = p->moments_alpha_min;
+    a.vacuous_mesh_id = (p->mesh_id_mode == SVGF_MESH_ID_REFERENCE_VACUOUS);
+    a.force_fail = c->force_fail_next ? 1 : 0;
+    // previous-frame guide: reuse the plane cached when `prev` was the current G-buffer
+    int prev_slot = -1;
+    if (!(p->flags & SVGF_FLAG_NO_GUIDE_CACHE))
+        for (int k = 0; k < 2; k++)
+            if (c->guide_key[k] == prev->motion_depth && c->guide_key[k] != nullptr) prev_slot = k;
+    // current-frame guide goes into the other slot
+    int cur_slot = (prev_slot >= 0) ? 1 - prev_slot : 1 - c->guide_cur;
+    if (c->guide_key[cur_slot] == prev->motion_depth) c->guide_key[cur_slot] = nullptr;
+    const dim3 grid = grid_for(c);
+    if (prev_slot >= 0)
+        temporal_kernel<F32, true><<<grid, 256, 0, s>>>(a, view(c, cur), view(c, prev), c->guide[prev_slot], c->guide[cur_slot],
+                                                        (const CT *)prev_colour, (CT *)cur_colour, hist_prev, hist_out,
+                                                        (MT *)cur_mom, (const MT *)prev_mom);
+    else
+        temporal_kernel<F32, false><<<grid, 256, 0, s>>>(a, view(c, cur), view(c, prev), nullptr, c->guide[cur_slot],
+                                                         (const CT *)prev_colour, (CT *)cur_colour, hist_prev, hist_out,
+                                                         (MT *)cur_mom, (const MT *)prev_mom);
+    c->launches++;
+    SVGF_CUDA(c, cudaGetLastError());
+    c->guide_key[cur_slot] = cur->motion_depth;
+    c->guide_cur = cur_slot;
+    c->force_fail_next = false;
+    return SVGF_OK;
+}
+
+SpatialArgs spatial_args(const svgf_ctx *c, const svgf_params *p, int level) {
+    SpatialArgs a;
+    a.W = c->W; a.H = c->H;
+    a.phi_colour = p->phi_colour; a.phi_normal = p->phi_normal; a.phi_depth = p->phi_depth;
+    a.step = 1 << level; a.level = level;
+    return a;
+}
+
+template <bool F32>
+svgf_status launch_variance(svgf_ctx *c, const svgf_params *p, int guide_slot, const void *in, const void *mom,
+                            const uint8_t *hist, uint8_t *hist_publish, void *out, cudaStream_t s) {
+    using CT = typename ColourPlane<F32>::texel;
+    using MT = typename MomentsPlane<F32>::texel;
+    variance_kernel<F32><<<grid_for(c), 256, 0, s>>>(spatial_args(c, p, 0), c->guide[guide_slot], (const CT *)in, (const MT *)mom,
+                                                     hist, hist_publish, (CT *)out);
+    c->launches++;
+    SVGF_CUDA(c, cudaGetLastError());
+    return SVGF_OK;
+}
+
+template <bool F32>
+svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slot, const void *in, void *out,
+                                void *hist_colour, int level, cudaStream_t s) {
+    using CT = typename ColourPlane<F32>::texel;
+    atrous_kernel<F32><<<grid_for(c), 256, 0, s>>>(spatial_args(c, p, level), c->guide[guide_slot], (const CT *)in, (CT *)out,
+                                                   (CT *)hist_colour);
+    c->launches++;
+    SVGF_CUDA(c, cudaGetLastError());
+    return SVGF_OK;
+}
+
+// Levels first..first+n-1, ping-ponging a -> b -> a ...; *result = last output (or `a` when n == 0).
+svgf_status run_atrous(svgf_ctx *c, const svgf_params *p, int guide_slot, void *a, void *b, void *hist_colour, int first,
+                       int n, void **result, cudaStream_t s) {
+    void *in = a, *out = b;
+    for (int l = first; l < first + n; l++) {
+        svgf_status st = (c->storage == SVGF_STORE_F32) ? launch_atrous_level<true>(c, p, guide_slot, in, out, hist_colour, l, s)
+                                                        : launch_atrous_level<false>(c, p, guide_slot, in, out, hist_colour, l, s);
+        if (st) return st;
+        void *t = in; in = out; out = t;
+    }
+    if (result) *result = in;
+    return SVGF_OK;
+}
+
+void prof_mark(svgf_ctx *c, int k, cudaStream_t s) {
+    if (c->profiling && c->prof_frames < svgf_ctx::kMaxProf) cudaEventRecord(c->prof_ev[c->prof_frames * 4 + k], s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int svgf_abi_version(void) { return SVGF_ABI_VERSION; }
+
+const char *svgf_status_string(svgf_status s) {
+    switch (s) {
+        case SVGF_OK: return "SVGF_OK";
+        case SVGF_INVALID_ARG: return "SVGF_INVALID_ARG";
+        case SVGF_UNSUPPORTED: return "SVGF_UNSUPPORTED";
+        case SVGF_CUDA_ERROR: return "SVGF_CUDA_ERROR";
+    }
+    return "SVGF_?";
+}
+
+void svgf_default_params(svgf_params *p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->history_cap = 24;          // reference src/App.h:112
+    p->depth_threshold = 0.8f;    // :110
+    p->normal_threshold = 0.9f;   // :111
+    p->phi_colour = 10.0f;        // :113
+    p->phi_normal = 128.0f;       // :114
+    p->atrous_iterations = 5;     // BASELINE.json (reference default 3, :109)
+    p->phi_depth = 1.0f;
+    p->alpha_min = 0.0f;
+    p->moments_alpha_min = 0.0f;
+    p->mesh_id_mode = SVGF_MESH_ID_INTENDED;
+    p->reproj_mode = SVGF_REPROJ_NEAREST_TRUNC;
+    p->variance_prefilter = SVGF_VARIANCE_PREFILTER_NONE;
+    p->flags = SVGF_FLAG_NONE;
+}
+
+svgf_status svgf_create(svgf_ctx **out, int device, int width, int height, svgf_storage storage) {
+    if (!out || width <= 0 || height <= 0 || width > 32768 || height > 32768) return SVGF_INVALID_ARG;
+    if (storage != SVGF_STORE_F16 && storage != SVGF_STORE_F32) return SVGF_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SVGF_CUDA_ERROR;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SVGF_CUDA_ERROR;
+    if (prop.major != 10) return SVGF_UNSUPPORTED;  // sm_100a only: no other code path exists in this library
+    DeviceGuard guard(device);
+    if (!guard.ok) return SVGF_CUDA_ERROR;
+    svgf_ctx *c = new (std::nothrow) svgf_ctx();
+    if (!c) return SVGF_CUDA_ERROR;
+    c->device = device; c->W = width; c->H = height; c->storage = storage;
+    const size_t n = (size_t)width * height;
+    cudaError_t e = cudaMalloc(&c->hist_shadow, n);
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaMalloc(&c->guide[k], n * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMemset(c->hist_shadow, 0, n);
+    if (e != cudaSuccess) { svgf_destroy(c); return SVGF_CUDA_ERROR; }
+    *out = c;
+    return SVGF_OK;
+}
+
+void svgf_destroy(svgf_ctx *c) {
+    if (!c) return;
+    DeviceGuard guard(c->device);
+    cudaFree(c->hist_shadow);
+    for (int k = 0; k < 2; k++) cudaFree(c->guide[k]);
+    if (c->prof_ev) {
+        for (int i = 0; i < svgf_ctx::kMaxProf * 4; i++) cudaEventDestroy(c->prof_ev[i]);
+        delete[] c->prof_ev;
+    }
+    for (int k = 0; k < 2; k++) {
+        cudaFree(c->hp.normal[k]); cudaFree(c->hp.uv[k]); cudaFree(c->hp.motion[k]);
+        cudaFree(c->hp.render[k]); cudaFree(c->hp.moments[k]); cudaFree(c->hp.filter[k]);
+    }
+    cudaFree(c->hp.history);
+    delete c;
+}
+
+int svgf_last_cuda_error(const svgf_ctx *c) { return c ? c->last_err : 0; }
+uint64_t svgf_launch_count(const svgf_ctx *c) { return c ? c->launches : 0; }
+
+void svgf_invalidate_guide(svgf_ctx *c) {
+    if (!c) return;
+    c->guide_key[0] = c->guide_key[1] = nullptr;
+}
+
+svgf_status svgf_reset(svgf_ctx *c, const svgf_frame_buffers *b, void *stream) {
+    if (!c) return SVGF_INVALID_ARG;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return SVGF_CUDA_ERROR;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (b) {
+        for (int k = 0; k < 2; k++) {
+            if (b->render[k]) SVGF_CUDA(c, cudaMemsetAsync(b->render[k], 0, colour_bytes(c), s));
+            if (b->moments[k]) SVGF_CUDA(c, cudaMemsetAsync(b->moments[k], 0, moments_bytes(c), s));
+        }
+        if (b->history) SVGF_CUDA(c, cudaMemsetAsync(b->history, 0, (size_t)c->W * c->H, s));
+    }
+    SVGF_CUDA(c, cudaMemsetAsync(c->hist_shadow, 0, (size_t)c->W * c->H, s));
+    svgf_invalidate_guide(c);
+    c->force_fail_next = true;
+    return SVGF_OK;
+}
+
+svgf_status svgf_temporal(svgf_ctx *c, const svgf_params *p, const svgf_gbuffer *cur, const svgf_gbuffer *prev,
+                          const void *prev_colour, void *cur_colour, uint8_t *history, void *cur_moments,
+                          const void *prev_moments, void *stream) {
+    if (!c) return SVGF_INVALID_ARG;
+    svgf_status st = check_params(p);
+    if (st) return st;
+    if ((st = check_gbuf(c, cur)) || (st = check_gbuf(c, prev))) return st;
+    if (!prev_colour || !cur_colour || !history || !cur_moments || !prev_moments || prev_colour == cur_colour ||
+        prev_moments == cur_moments)
+        return SVGF_INVALID_ARG;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return SVGF_CUDA_ERROR;
+    cudaStream_t s = (cudaStream_t)stream;
+    st = (c->storage == SVGF_STORE_F32)
+             ? launch_temporal<true>(c, p, cur, prev, prev_colour, cur_colour, history, c->hist_shadow, cur_moments, prev_moments, s)
+             : launch_temporal<false>(c, p, cur, prev, prev_colour, cur_colour, history, c->hist_shadow, cur_moments, prev_moments, s);
+    if (st) return st;
+    // publish: the caller-visible plane now holds this frame's lengths
+    SVGF_CUDA(c, cudaMemcpyAsync(history, c->hist_shadow, (size_t)c->W * c->H, cudaMemcpyDeviceToDevice, s));
+    return SVGF_OK;
+}
+
+svgf_status svgf_variance(svgf_ctx *c, const svgf_params *p, const svgf_gbuffer *cur, const void *colour_in,
+                          const void *moments, const uint8_t *history, void *colour_out, void *stream) {
+    if (!c) return SVGF_INVALID_ARG;
+    svgf_status st = check_params(p);
+    if (st) return st;
+    if ((st = check_gbuf(c, cur))) return st;
+    if (!colour_in || !moments || !history || !colour_out || colour_in == colour_out) return SVGF_INVALID_ARG;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return SVGF_CUDA_ERROR;
+    cudaStream_t s = (cudaStream_t)stream;
+    int slot;
+    if ((st = ensure_guide(c, cur, s, &slot))) return st;
+    return (c->storage == SVGF_STORE_F32) ? launch_variance<true>(c, p, slot, colour_in, moments, history, nullptr, colour_out, s)
+                                          : launch_variance<false>(c, p, slot, colour_in, moments, history, nullptr, colour_out, s);
+}
+
+svgf_status svgf_atrous(svgf_ctx *c, const svgf_params *p, const svgf_gbuffer *cur, void *buf_a, void *buf_b,
+                        void *history_colour_out, int first_level, int num_levels, void **result, void *stream) {
+    if (!c) return SVGF_INVALID_ARG;
+    svgf_status st = check_params(p);
+    if (st) return st;
+    if ((st = check_gbuf(c, cur))) return st;
+    if (!buf_a || !buf_b || buf_a == buf_b || first_level < 0 || num_levels < 0 || first_level + num_levels > 11)
+        return SVGF_INVALID_ARG;
+    if (history_colour_out == buf_a || history_colour_out == buf_b) return SVGF_INVALID_ARG;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return SVGF_CUDA_ERROR;
+    cudaStream_t s = (cudaStream_t)stream;
+    int slot;
+    if ((st = ensure_guide(c, cur, s, &slot))) return st;
+    return run_atrous(c, p, slot, buf_a, buf_b, history_colour_out, first_level, num_levels, result, s);
+}
+
+svgf_status svgf_frame(svgf_ctx *c, const svgf_params *p, const svgf_gbuffer gbuf[2], const svgf_frame_buffers *b,
+                       void *stream) {
+    if (!c || !gbuf || !b) return SVGF_INVALID_ARG;
+    svgf_status st = check_params(p);
+    if (st) return st;
+    if (b->ping_pong != 0 && b->ping_pong != 1) return SVGF_INVALID_ARG;
+    const int P = b->ping_pong, Q = 1 - P;
+    if ((st = check_gbuf(c, &gbuf[P])) || (st = check_gbuf(c, &gbuf[Q]))) return st;
+    for (int k = 0; k < 2; k++)
+        if (!b->render[k] || !b->moments[k] || !b->filter[k]) return SVGF_INVALID_ARG;
+    if (!b->history || b->render[0] == b->render[1] || b->moments[0] == b->moments[1] || b->filter[0] == b->filter[1])
+        return SVGF_INVALID_ARG;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return SVGF_CUDA_ERROR;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool f32 = (c->storage == SVGF_STORE_F32);
+
+    prof_mark(c, 0, s);
+    // temporal: reads the caller-visible history plane (previous frame), writes the shadow plane
+    st = f32 ? launch_temporal<true>(c, p, &gbuf[P], &gbuf[Q], b->render[Q], b->render[P], b->history, c->hist_shadow,
+                                     b->moments[P], b->moments[Q], s)
+             : launch_temporal<false>(c, p, &gbuf[P], &gbuf[Q], b->render[Q], b->render[P], b->history, c->hist_shadow,
+                                      b->moments[P], b->moments[Q], s);
+    if (st) return st;
+    prof_mark(c, 1, s);
+    // variance -> filter[N & 1] so that N ping-pong levels end in filter[0] (the reference copies instead,
+    // src/App.cu:510-513); it also publishes the history plane.
+    const int N = p->atrous_iterations;
+    void *v_out = b->filter[N & 1], *other = b->filter[1 - (N & 1)];
+    const int slot = c->guide_cur;
+    st = f32 ? launch_variance<true>(c, p, slot, b->render[P], b->moments[P], c->hist_shadow, b->history, v_out, s)
+             : launch_variance<false>(c, p, slot, b->render[P], b->moments[P], c->hist_shadow, b->history, v_out, s);
+    if (st) return st;
+    prof_mark(c, 2, s);
+    void *result = nullptr;
+    st = run_atrous(c, p, slot, v_out, other, b->render[P], 0, N, &result, s);
+    if (st) return st;
+    prof_mark(c, 3, s);
+    if (c->profiling && c->prof_frames < svgf_ctx::kMaxProf) c->prof_frames++;
+    return (result == b->filter[0]) ? SVGF_OK : SVGF_CUDA_ERROR;  // invariant of the rotation above
+}
+
+// ---- stage profiling -----------------------------------------------------------------------------------------
+// Between svgf_profile_begin and svgf_profile_end every svgf_frame records four CUDA events on the caller's
+// stream (before temporal, before variance, before a-trous, after a-trous).  svgf_profile_end synchronises
+// the last event and returns the summed GPU milliseconds per stage and the number of frames captured.
+svgf_status svgf_profile_begin(svgf_ctx *c) {
+    if (!c) return SVGF_INVALID_ARG;
+    DeviceGuard guard(c->device);
+    if (!c->prof_ev) {
+        c->prof_ev = new (std::nothrow) cudaEvent_t[svgf_ctx::kMaxProf * 4];
+        if (!c->prof_ev) return SVGF_CUDA_ERROR;
+        for (int i = 0; i < svgf_ctx::kMaxProf * 4; i++) SVGF_CUDA(c, cudaEventCreate(&c->prof_ev[i]));
+    }
+    c->prof_frames = 0;
+    c->profiling = true;
+    return SVGF_OK;
+}
+
+svgf_status svgf_profile_end(svgf_ctx *c, double stage_ms[3], int *frames) {
+    if (!c || !c->profiling) return SVGF_INVALID_ARG;
+    DeviceGuard guard(c->device);
+    c->profiling = false;
+    double acc[3] = {0, 0, 0};
+    if (c->prof_frames > 0) SVGF_CUDA(c, cudaEventSynchronize(c->prof_ev[(c->prof_frames - 1) * 4 + 3]));
+    for (int f = 0; f < c->prof_frames; f++)
+        for (int k = 0; k < 3; k++) {
+            float ms = 0.f;
+            SVGF_CUDA(c, cudaEventElapsedTime(&ms, c->prof_ev[f * 4 + k], c->prof_ev[f * 4 + k + 1]));
+            acc[k] += ms;
+        }
+    if (stage_ms) for (int k = 0; k < 3; k++) stage_ms[k] = acc[k];
+    if (frames) *frames = c->prof_frames;
+    return SVGF_OK;
+}
+
+// ---- host-buffer path ----------------------------------------------------------------------------------------
+svgf_status svgf_frame_host(svgf_ctx *c, const svgf_params *p, const void *h_normal, const void *h_uv, const void *h_motion,
+                            const void *h_colour, void *h_result, uint8_t *h_history_out, int reset, void *stream) {
+    if (!c || !h_normal || !h_uv || !h_motion || !h_colour) return SVGF_INVALID_ARG;
+    svgf_status st = check_params(p);
+    if (st) return st;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return SVGF_CUDA_ERROR;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)c->W * c->H;
+    svgf_ctx::HostPath &hp = c->hp;
+    if (!hp.ready) {
+        for (int k = 0; k < 2; k++) {
+            SVGF_CUDA(c, cudaMalloc(&hp.normal[k], n * 8));
+            SVGF_CUDA(c, cudaMalloc(&hp.uv[k], n * 8));
+            SVGF_CUDA(c, cudaMalloc(&hp.motion[k], n * 16));
+            SVGF_CUDA(c, cudaMalloc(&hp.render[k], colour_bytes(c)));
+            SVGF_CUDA(c, cudaMalloc(&hp.moments[k], moments_bytes(c)));
+            SVGF_CUDA(c, cudaMalloc(&hp.filter[k], colour_bytes(c)));
+        }
+        SVGF_CUDA(c, cudaMalloc(&hp.history, n));
+        hp.ready = true;
+        reset = 1;
+    }
+    svgf_frame_buffers b;
+    for (int k = 0; k < 2; k++) { b.render[k] = hp.render[k]; b.moments[k] = hp.moments[k]; b.filter[k] = hp.filter[k]; }
+    b.history = hp.history;
+    if (reset) {
+        hp.ping_pong = 0;
+        if ((st = svgf_reset(c, &b, s))) return st;
+    }
+    const int P = hp.ping_pong;
+    b.ping_pong = P;
+    SVGF_CUDA(c, cudaMemcpyAsync(hp.normal[P], h_normal, n * 8, cudaMemcpyHostToDevice, s));
+    SVGF_CUDA(c, cudaMemcpyAsync(hp.uv[P], h_uv, n * 8, cudaMemcpyHostToDevice, s));
+    SVGF_CUDA(c, cudaMemcpyAsync(hp.motion[P], h_motion, n * 16, cudaMemcpyHostToDevice, s));
+    SVGF_CUDA(c, cudaMemcpyAsync(hp.render[P], h_colour, colour_bytes(c), cudaMemcpyHostToDevice, s));
+    svgf_gbuffer g[2];
+    for (int k = 0; k < 2; k++) {
+        g[k].position_id = nullptr; g[k].position_pitch = 0;
+        g[k].normal_mat = hp.normal[k]; g[k].normal_pitch = 0;
+        g[k].uv_inst = hp.uv[k]; g[k].uv_pitch = 0;
+        g[k].motion_depth = hp.motion[k]; g[k].motion_pitch = 0;
+    }
+    // the G-buffer contents of slot P have just changed under the same pointer
+    for (int k = 0; k < 2; k++)
+        if (c->guide_key[k] == hp.motion[P]) c->guide_key[k] = nullptr;
+    if ((st = svgf_frame(c, p, g, &b, s))) return st;
+    if (h_result) SVGF_CUDA(c, cudaMemcpyAsync(h_result, hp.filter[0], colour_bytes(c), cudaMemcpyDeviceToHost, s));
+    if (h_history_out) SVGF_CUDA(c, cudaMemcpyAsync(h_history_out, hp.history, n, cudaMemcpyDeviceToHost, s));
+    hp.ping_pong = 1 - P;
+    return SVGF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,211 @@
+// svgf_kernels_basic.cuh — one-thread-per-pixel sm_100a kernels for every stage of the path.  These are the
+// simple, always-correct variants: used for resolutions / parameter combinations the tiled kernels do not
+// cover and as the in-library A/B baseline.  The optimised kernels live in svgf_kernels_tiled.cuh.
+#pragma once
+#include "svgf_device.cuh"
+
+namespace svgf {
+
+struct GBufView {  // pitch-linear G-buffer planes (include/svgf.h svgf_gbuffer), pitches in bytes
+    const char *normal, *uv, *motion;
+    size_t normal_pitch, uv_pitch, motion_pitch;
+    __device__ __forceinline__ float4 mot(int x, int y) const {
+        return __ldg(reinterpret_cast<const float4 *>(motion + (size_t)y * motion_pitch) + x);
+    }
+    __device__ __forceinline__ ushort4 nrm(int x, int y) const {
+        return __ldg(reinterpret_cast<const ushort4 *>(normal + (size_t)y * normal_pitch) + x);
+    }
+    __device__ __forceinline__ ushort4 uvw(int x, int y) const {
+        return __ldg(reinterpret_cast<const ushort4 *>(uv + (size_t)y * uv_pitch) + x);
+    }
+};
+
+struct TemporalArgs {
+    int W, H;
+    float depth_threshold, normal_threshold;
+    int history_cap;
+    float alpha_min, moments_alpha_min;
+    int vacuous_mesh_id;   // svgf_mesh_id_mode == REFERENCE_VACUOUS
+    int force_fail;        // first frame after svgf_reset: every reprojection fails (D12)
+};
+
+// ---- build the compact guide plane from a G-buffer (used when a stage is called on a G-buffer the temporal
+// pass has not seen) ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) build_guide_kernel(GBufView g, float4 *__restrict__ guide, int W, int H) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    guide[(size_t)y * W + x] = make_guide(g.mot(x, y), g.nrm(x, y), g.uvw(x, y));
+}
+
+// ---- temporal reprojection + accumulation: reference filter::TemporalFilter (src/Filter.cuh:359-404) with
+// LoadPreviousData (:225-258).  PREV_GUIDE: previous-frame consistency data comes from the compact guide
+// plane cached by the previous frame instead of the three previous G-buffer planes.
+template <bool F32, bool PREV_GUIDE>
+__global__ void __launch_bounds__(256)
+temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, const float4 *__restrict__ prev_guide,
+                float4 *__restrict__ cur_guide, const typename ColourPlane<F32>::texel *__restrict__ prev_colour,
+                typename ColourPlane<F32>::texel *colour, const uint8_t *__restrict__ hist_prev, uint8_t *__restrict__ hist_out,
+                typename MomentsPlane<F32>::texel *__restrict__ cur_mom,
+                const typename MomentsPlane<F32>::texel *__restrict__ prev_mom) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= a.W || y >= a.H) return;
+    const size_t i = (size_t)y * a.W + x;
+
+    const float4 mv = cur.mot(x, y);
+    const float4 g = make_guide(mv, cur.nrm(x, y), cur.uvw(x, y));
+    cur_guide[i] = g;
+    const float4 c = clamp01(ColourPlane<F32>::decode(colour[i]));            // :370
+
+    float3 pc = make_float3(0.f, 0.f, 0.f);
+    float2 pm = make_float2(0.f, 0.f);
+    int h = 1;
+    bool ok = false;
+    const int qx = x + __float2int_rz(mv.x), qy = y + __float2int_rz(mv.y);    // :232
+    if (!a.force_fail && qx >= 0 && qx < a.W && qy >= 0 && qy < a.H) {         // :235
+        const size_t qi = (size_t)qy * a.W + qx;
+        float4 pg;
+        if (PREV_GUIDE) pg = __ldg(prev_guide + qi);
+        else pg = make_guide(prev.mot(qx, qy), prev.nrm(qx, qy), prev.uvw(qx, qy));
+        ok = !(fabsf(pg.x - g.x) > a.depth_threshold);                         // :242
+        ok = ok && (a.vacuous_mesh_id || guide_mesh_id(g) == guide_mesh_id(pg));  // :245-247
+        ok = ok && !(dot3(guide_normal(g), guide_normal(pg)) < a.normal_threshold);  // :250-252
+        if (ok) {
+            const float4 p4 = clamp01(ColourPlane<F32>::decode(__ldg(prev_colour + qi)));  // :254
+            pc = make_float3(p4.x, p4.y, p4.z);
+            h = hist_prev[qi];                                                 // :255 (snapshot plane)
+            pm = MomentsPlane<F32>::decode(__ldg(prev_mom + qi));              // :256
+        }
+    }
+    float alpha = 1.0f, alpha_m = 1.0f;
+    if (ok) {
+        h = min(a.history_cap, h + 1);                                         // :380
+        const float inv = __fdiv_rn(1.0f, (float)h);                          // :381 (== float(1.0/h) for h <= 255, tests/test_oracle_kat.py)
+        alpha = fmaxf(inv, a.alpha_min);
+        alpha_m = fmaxf(inv, a.moments_alpha_min);
+    } else {
+        h = 1;
+    }
+    const float L = luminance(c.x, c.y, c.z);                                  // :391
+    float2 m;
+    m.x = pm.x * (1.0f - alpha_m) + L * alpha_m;                               // :393 glm::mix
+    m.y = pm.y * (1.0f - alpha_m) + (L * L) * alpha_m;
+    const float var = fmaxf(0.0f, m.y - m.x * m.x);                            // :396
+    float4 o;
+    o.x = pc.x * (1.0f - alpha) + c.x * alpha;                                 // :398
+    o.y = pc.y * (1.0f - alpha) + c.y * alpha;
+    o.z = pc.z * (1.0f - alpha) + c.z * alpha;
+    o.w = var;
+    hist_out[i] = (uint8_t)h;                                                  // :400
+    colour[i] = ColourPlane<F32>::encode(clamp01(o));                          // :401
+    cur_mom[i] = MomentsPlane<F32>::encode(m);                                 // :402
+}
+
+struct SpatialArgs {
+    int W, H;
+    float phi_colour, phi_normal, phi_depth;
+    int step, level;
+};
+
+// ---- variance estimation: reference filter::FilterMoments (src/Filter.cuh:430-525).  Also publishes the
+// history plane (hist_publish, may be null): the caller-visible buffer receives this frame's lengths here so
+// the temporal pass never reads and writes one plane in the same launch (D3).
+template <bool F32>
+__global__ void __launch_bounds__(256)
+variance_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename ColourPlane<F32>::texel *__restrict__ in,
+                const typename MomentsPlane<F32>::texel *__restrict__ mom, const uint8_t *__restrict__ hist,
+                uint8_t *__restrict__ hist_publish, typename ColourPlane<F32>::texel *__restrict__ out) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= a.W || y >= a.H) return;
+    const size_t i = (size_t)y * a.W + x;
+    const uint8_t hb = hist[i];
+    if (hist_publish) hist_publish[i] = hb;
+    if (hb >= 4) {                                                             // :444,:518-523
+        out[i] = in[i];
+        return;
+    }
+    const float h = (float)hb;
+    const float4 cc = ColourPlane<F32>::decode(__ldg(in + i));                 // :450 (no clamp)
+    const float lc = luminance(cc.x, cc.y, cc.z);
+    const float4 gc = __ldg(guide + i);
+    const float3 nc = guide_normal(gc);
+    const float kL = kLog2e / a.phi_colour;                                    // :460
+    const float phiZ0 = fmaxf(gc.y, 1e-8f) * 3.0f * a.phi_depth;              // :461
+    float sw = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sm1 = 0.f, sm2 = 0.f;
+    for (int yy = -3; yy <= 3; yy++) {
+        const int py = y + yy;
+        if (py < 0 || py >= a.H) continue;
+        for (int xx = -3; xx <= 3; xx++) {
+            const int px = x + xx;
+            if (px < 0 || px >= a.W) continue;                                 // :473
+            const size_t qi = (size_t)py * a.W + px;
+            const float4 cq = ColourPlane<F32>::decode(__ldg(in + qi));
+            const float2 mq = MomentsPlane<F32>::decode(__ldg(mom + qi));
+            const float4 gq = __ldg(guide + qi);
+            const float lq = luminance(cq.x, cq.y, cq.z);
+            const float phiZ = phiZ0 * sqrtf((float)(xx * xx + yy * yy));      // :488
+            const float kZ = (phiZ == 0.0f) ? 0.0f : kLog2e / phiZ;            // :420
+            const float e = edge_weight_log2(fabsf(lc - lq) * kL, fabsf(gc.x - gq.x) * kZ, dot3(nc, guide_normal(gq)), 0.25f * a.phi_normal);
+            const float w = fast_exp2(e);
+            sw += w;                                                           // :497-499
+            sr += cq.x * w; sg += cq.y * w; sb += cq.z * w;
+            sm1 += mq.x * w; sm2 += mq.y * w;
+        }
+    }
+    sw = fmaxf(sw, 1e-6f);                                                     // :505
+    const float inv = 1.0f / sw;
+    const float m1 = sm1 * inv, m2 = sm2 * inv;
+    float var = m2 - m1 * m1;                                                  // :511
+    var = var * (4.0f / h);                                                    // :514  (h in {0,1,2,3}; h == 0 only if the caller supplies it)
+    out[i] = ColourPlane<F32>::encode(make_float4(sr * inv, sg * inv, sb * inv, var));  // :516
+}
+
+// ---- one a-trous level: reference filter::FilterKernel (src/Filter.cuh:527-624) ---------------------------
+template <bool F32>
+__global__ void __launch_bounds__(256)
+atrous_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename ColourPlane<F32>::texel *__restrict__ in,
+              typename ColourPlane<F32>::texel *__restrict__ out, typename ColourPlane<F32>::texel *__restrict__ hist_colour) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= a.W || y >= a.H) return;
+    const size_t i = (size_t)y * a.W + x;
+    const float4 c = clamp01(ColourPlane<F32>::decode(__ldg(in + i)));         // :543
+    const float4 gc = __ldg(guide + i);
+    if (gc.x == kBackgroundZ) {                                                // :554-558
+        out[i] = ColourPlane<F32>::encode(c);
+        return;
+    }
+    const float lc = luminance(c.x, c.y, c.z);
+    const float3 nc = guide_normal(gc);
+    const float phiL = a.phi_colour * sqrtf(fmaxf(0.0f, 1e-10f + c.w));        // :562
+    const float kL = kLog2e / phiL;
+    const float phiZ = fmaxf(gc.y, 1e-6f) * (float)a.step * a.phi_depth;       // :563
+    const float kZ1 = (phiZ == 0.0f) ? 0.0f : kLog2e / phiZ;
+    const float KW[3] = {1.0f, (float)(2.0 / 3.0), (float)(1.0 / 6.0)};        // :540
+    float sw = 1.0f, sr = c.x, sg = c.y, sb = c.z, sv = c.w;                   // :567-568
+#pragma unroll
+    for (int yy = -2; yy <= 2; yy++) {
+        const int py = y + yy * a.step;
+        if (py < 0 || py >= a.H) continue;
+#pragma unroll
+        for (int xx = -2; xx <= 2; xx++) {
+            const int px = x + xx * a.step;
+            if (px < 0 || px >= a.W || (xx == 0 && yy == 0)) continue;         // :579,:584
+            const size_t qi = (size_t)py * a.W + px;
+            const float4 cq = clamp01(ColourPlane<F32>::decode(__ldg(in + qi)));  // :586
+            const float4 gq = __ldg(guide + qi);
+            const float lq = luminance(cq.x, cq.y, cq.z);
+            const float kZ = kZ1 / sqrtf((float)(xx * xx + yy * yy));          // phiZ * length(xx,yy), :595
+            const float e = edge_weight_log2(fabsf(lc - lq) * kL, fabsf(gc.x - gq.x) * kZ, dot3(nc, guide_normal(gq)), 0.25f * a.phi_normal);
+            const float w = fast_exp2(e) * (KW[xx < 0 ? -xx : xx] * KW[yy < 0 ? -yy : yy]);  // :604
+            sw += w;                                                           // :607-608
+            sr += w * cq.x; sg += w * cq.y; sb += w * cq.z;
+            sv += (w * w) * cq.w;
+        }
+    }
+    const float inv = 1.0f / sw;
+    const typename ColourPlane<F32>::texel o =
+        ColourPlane<F32>::encode(make_float4(sr * inv, sg * inv, sb * inv, sv * (inv * inv)));  // :615
+    out[i] = o;                                                                // :618
+    if (a.level == 0 && hist_colour) hist_colour[i] = o;                       // :619-622
+}
+
+}  // namespace svgf

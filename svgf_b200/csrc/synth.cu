@@ -1,0 +1,74 @@
+// synth.cu — C entry points of the procedural input generator (libsvgf_synth.so): the same per-pixel
+// function (synth_scene.h) run either by a CUDA kernel into device planes or by an OpenMP loop into host
+// planes.  Compiled with -fmad=false / -ffp-contract=off so both produce identical bits.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <omp.h>
+#include <string.h>
+
+#include "synth_scene.h"
+
+namespace {
+
+struct Planes {
+    float4 *position;   // may be null
+    ushort4 *normal;
+    ushort4 *uv;
+    float4 *motion;
+    void *colour;       // half4 bits (ushort4) or float4
+};
+
+SYNTH_HD void store_texel(const Planes &pl, size_t i, const synth::Texel &t, int storage) {
+    if (pl.position) pl.position[i] = make_float4(t.pos[0], t.pos[1], t.pos[2], t.pos[3]);
+    if (pl.normal) pl.normal[i] = make_ushort4(t.nrm[0], t.nrm[1], t.nrm[2], t.nrm[3]);
+    if (pl.uv) pl.uv[i] = make_ushort4(t.uv[0], t.uv[1], t.uv[2], t.uv[3]);
+    if (pl.motion) pl.motion[i] = make_float4(t.mot[0], t.mot[1], t.mot[2], t.mot[3]);
+    if (pl.colour) {
+        if (storage == 1) {
+            ((float4 *)pl.colour)[i] = make_float4(t.col[0], t.col[1], t.col[2], t.col[3]);
+        } else {
+            ((ushort4 *)pl.colour)[i] = make_ushort4(synth::f2h_bits(t.col[0]), synth::f2h_bits(t.col[1]),
+                                                     synth::f2h_bits(t.col[2]), synth::f2h_bits(t.col[3]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(svgf_synth_cfg cfg, Planes pl) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= cfg.width || y >= cfg.height) return;
+    const synth::Texel t = synth::shade_pixel(cfg, x, y);
+    store_texel(pl, (size_t)y * cfg.width + x, t, cfg.storage);
+}
+
+bool cfg_ok(const svgf_synth_cfg *c) {
+    return c && c->width > 0 && c->height > 0 && c->frame >= 0 && (c->storage == 0 || c->storage == 1);
+}
+
+}  // namespace
+
+extern "C" {
+
+// Host planes, dense (pitch = W * texel).  Any plane pointer may be NULL to skip it.  threads <= 0: all cores.
+int svgf_synth_frame_host(const svgf_synth_cfg *cfg, void *position, void *normal, void *uv, void *motion, void *colour,
+                          int threads) {
+    if (!cfg_ok(cfg)) return 1;
+    Planes pl{(float4 *)position, (ushort4 *)normal, (ushort4 *)uv, (float4 *)motion, colour};
+    const svgf_synth_cfg c = *cfg;
+#pragma omp parallel for schedule(dynamic, 8) num_threads(threads > 0 ? threads : omp_get_max_threads())
+    for (int y = 0; y < c.height; y++)
+        for (int x = 0; x < c.width; x++) store_texel(pl, (size_t)y * c.width + x, synth::shade_pixel(c, x, y), c.storage);
+    return 0;
+}
+
+// Device planes; asynchronous on `stream` (cudaStream_t).  Returns a cudaError_t as int.
+int svgf_synth_frame_device(const svgf_synth_cfg *cfg, void *position, void *normal, void *uv, void *motion, void *colour,
+                            void *stream) {
+    if (!cfg_ok(cfg)) return 1;
+    Planes pl{(float4 *)position, (ushort4 *)normal, (ushort4 *)uv, (float4 *)motion, colour};
+    dim3 grid((cfg->width + 31) / 32, (cfg->height + 7) / 8);
+    synth_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*cfg, pl);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"
