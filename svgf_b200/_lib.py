@@ -79,6 +79,7 @@ ABI = [
 
 SYNTH_ABI = [
     ("svgf_synth_frame_host", C.c_int, [C.POINTER(SynthCfg)] + [C.c_void_p] * 5 + [C.c_int]),
+    ("svgf_synth_rows_host", C.c_int, [C.POINTER(SynthCfg), C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int]),
     ("svgf_synth_frame_device", C.c_int, [C.POINTER(SynthCfg)] + [C.c_void_p] * 6),
 ]
 

@@ -53,8 +53,17 @@ template <> struct MomentsPlane<true> {
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 __device__ __forceinline__ float4 clamp01(float4 v) { return make_float4(clamp01(v.x), clamp01(v.y), clamp01(v.z), clamp01(v.w)); }
 
-// CalculateLuminance, src/Filter.cuh:260-263
-__device__ __forceinline__ float luminance(float r, float g, float b) { return 0.2126f * r + 0.7152f * g + 0.0722f * b; }
+// CalculateLuminance, src/Filter.cuh:260-263.  Deliberately NOT contracted into FMAs: with a centre
+// variance near 0 the luminance edge-stopping scale is phi*1e-5, so the weights amplify luminance rounding
+// differences by ~1e4; each product and sum rounds once, left to right, exactly like the scalar oracle.
+// Luminance is computed once per pixel (never per tap), so the two extra instructions are free.
+__device__ __forceinline__ float luminance(float r, float g, float b) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, r), __fmul_rn(0.7152f, g)), __fmul_rn(0.0722f, b));
+}
+// glm::mix(x, y, a) = x*(1-a) + y*a without contraction (temporal pass: bit-exact against the oracle)
+__device__ __forceinline__ float mix_rn(float x, float y, float a) {
+    return __fadd_rn(__fmul_rn(x, __fsub_rn(1.0f, a)), __fmul_rn(y, a));
+}
 
 // ---- compact guide texel (16 B): everything the consistency tests and edge-stopping functions need from
 // the three G-buffer planes (motion.zw, normal.xyz, uv.w = 32 B of texels), emitted once per frame by the

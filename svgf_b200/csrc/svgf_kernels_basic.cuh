@@ -87,13 +87,13 @@ temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, const float4 *__res
     }
     const float L = luminance(c.x, c.y, c.z);                                  // :391
     float2 m;
-    m.x = pm.x * (1.0f - alpha_m) + L * alpha_m;                               // :393 glm::mix
-    m.y = pm.y * (1.0f - alpha_m) + (L * L) * alpha_m;
-    const float var = fmaxf(0.0f, m.y - m.x * m.x);                            // :396
+    m.x = mix_rn(pm.x, L, alpha_m);                                            // :393 glm::mix
+    m.y = mix_rn(pm.y, __fmul_rn(L, L), alpha_m);
+    const float var = fmaxf(0.0f, __fsub_rn(m.y, __fmul_rn(m.x, m.x)));        // :396
     float4 o;
-    o.x = pc.x * (1.0f - alpha) + c.x * alpha;                                 // :398
-    o.y = pc.y * (1.0f - alpha) + c.y * alpha;
-    o.z = pc.z * (1.0f - alpha) + c.z * alpha;
+    o.x = mix_rn(pc.x, c.x, alpha);                                            // :398
+    o.y = mix_rn(pc.y, c.y, alpha);
+    o.z = mix_rn(pc.z, c.z, alpha);
     o.w = var;
     hist_out[i] = (uint8_t)h;                                                  // :400
     colour[i] = ColourPlane<F32>::encode(clamp01(o));                          // :401

@@ -61,6 +61,19 @@ int svgf_synth_frame_host(const svgf_synth_cfg *cfg, void *position, void *norma
     return 0;
 }
 
+// Rows [y0, y1) of the frame only, into host planes of (y1 - y0) x W texels (bounded CPU samples of large frames).
+int svgf_synth_rows_host(const svgf_synth_cfg *cfg, int y0, int y1, void *position, void *normal, void *uv, void *motion,
+                         void *colour, int threads) {
+    if (!cfg_ok(cfg) || y0 < 0 || y1 > cfg->height || y0 >= y1) return 1;
+    Planes pl{(float4 *)position, (ushort4 *)normal, (ushort4 *)uv, (float4 *)motion, colour};
+    const svgf_synth_cfg c = *cfg;
+#pragma omp parallel for schedule(dynamic, 8) num_threads(threads > 0 ? threads : omp_get_max_threads())
+    for (int y = y0; y < y1; y++)
+        for (int x = 0; x < c.width; x++)
+            store_texel(pl, (size_t)(y - y0) * c.width + x, synth::shade_pixel(c, x, y), c.storage);
+    return 0;
+}
+
 // Device planes; asynchronous on `stream` (cudaStream_t).  Returns a cudaError_t as int.
 int svgf_synth_frame_device(const svgf_synth_cfg *cfg, void *position, void *normal, void *uv, void *motion, void *colour,
                             void *stream) {

@@ -15,24 +15,27 @@ def make_cfg(width, height, frame, seed=0, storage="f16", pan_px=PAN_PX, vert_px
     return SynthCfg(width, height, seed, frame, pan_px, vert_px, half_period, 0 if storage == "f16" else 1)
 
 
-def frame_host(width, height, frame, seed=0, storage="f16", with_position=False, threads=0, **kw):
+def frame_host(width, height, frame, seed=0, storage="f16", with_position=False, threads=0, rows=None, **kw):
     """Returns dict of numpy planes: normal/uv (uint16 [H,W,4]), motion (float32 [H,W,4]),
-    colour (float16|float32 [H,W,4]) and optionally position."""
+    colour (float16|float32 [H,W,4]) and optionally position.  rows=(y0, y1) generates only that band of the
+    frame (planes are then [y1-y0, W, 4])."""
     cfg = make_cfg(width, height, frame, seed, storage, **kw)
+    y0, y1 = rows if rows is not None else (0, height)
+    h = y1 - y0
     out = {
-        "normal": np.empty((height, width, 4), np.uint16),
-        "uv": np.empty((height, width, 4), np.uint16),
-        "motion": np.empty((height, width, 4), np.float32),
-        "colour": np.empty((height, width, 4), np.float16 if storage == "f16" else np.float32),
+        "normal": np.empty((h, width, 4), np.uint16),
+        "uv": np.empty((h, width, 4), np.uint16),
+        "motion": np.empty((h, width, 4), np.float32),
+        "colour": np.empty((h, width, 4), np.float16 if storage == "f16" else np.float32),
     }
-    pos = np.empty((height, width, 4), np.float32) if with_position else None
+    pos = np.empty((h, width, 4), np.float32) if with_position else None
     if with_position:
         out["position"] = pos
-    rc = _lib.synth_lib().svgf_synth_frame_host(
-        C.byref(cfg), pos.ctypes.data if with_position else None, out["normal"].ctypes.data, out["uv"].ctypes.data,
+    rc = _lib.synth_lib().svgf_synth_rows_host(
+        C.byref(cfg), y0, y1, pos.ctypes.data if with_position else None, out["normal"].ctypes.data, out["uv"].ctypes.data,
         out["motion"].ctypes.data, out["colour"].ctypes.data, threads)
     if rc:
-        raise RuntimeError(f"svgf_synth_frame_host failed ({rc})")
+        raise RuntimeError(f"svgf_synth_rows_host failed ({rc})")
     return out
 
 
