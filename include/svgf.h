@@ -68,6 +68,8 @@ typedef enum svgf_variance_prefilter { SVGF_VARIANCE_PREFILTER_NONE = 0 } svgf_v
 #define SVGF_FLAG_NO_GUIDE_CACHE 1u
 /* svgf_frame / svgf_atrous: run every a-trous level as its own launch (disables two-level fusion). */
 #define SVGF_FLAG_NO_LEVEL_FUSION 2u
+/* Run every stage with the simple one-thread-per-pixel kernels instead of the tiled ones (A/B baseline). */
+#define SVGF_FLAG_BASIC_KERNELS 4u
 
 /* Tunables.  Defaults (svgf_default_params) are the reference's members src/App.h:109-114, GUI ranges
  * src/GUI.cpp:988-993.  phi_depth / alpha_min / moments_alpha_min are additions whose defaults

@@ -9,6 +9,7 @@
 
 #include "../../include/svgf.h"
 #include "svgf_kernels_basic.cuh"
+#include "svgf_kernels_tiled.cuh"
 
 using namespace svgf;
 
@@ -63,7 +64,6 @@ svgf_status check_params(const svgf_params *p) {
     if (p->mesh_id_mode != SVGF_MESH_ID_INTENDED && p->mesh_id_mode != SVGF_MESH_ID_REFERENCE_VACUOUS) return SVGF_INVALID_ARG;
     if (p->reproj_mode != SVGF_REPROJ_NEAREST_TRUNC) return SVGF_UNSUPPORTED;
     if (p->variance_prefilter != SVGF_VARIANCE_PREFILTER_NONE) return SVGF_UNSUPPORTED;
-    if (p->phi_normal > 0.0f && p->phi_normal < 1.0f) return SVGF_UNSUPPORTED;  // see edge_weight_log2
     return SVGF_OK;
 }
 
@@ -155,7 +155,8 @@ svgf_status launch_temporal(svgf_ctx *c, const svgf_params *p, const svgf_gbuffe
 SpatialArgs spatial_args(const svgf_ctx *c, const svgf_params *p, int level) {
     SpatialArgs a;
     a.W = c->W; a.H = c->H;
-    a.phi_colour = p->phi_colour; a.phi_normal = p->phi_normal; a.phi_depth = p->phi_depth;
+    a.phi_colour = p->phi_colour; a.phi_depth = p->phi_depth;
+    a.nt = make_normal_term(p->phi_normal);
     a.step = 1 << level; a.level = level;
     return a;
 }
@@ -165,19 +166,68 @@ svgf_status launch_variance(svgf_ctx *c, const svgf_params *p, int guide_slot, c
                             const uint8_t *hist, uint8_t *hist_publish, void *out, cudaStream_t s) {
     using CT = typename ColourPlane<F32>::texel;
     using MT = typename MomentsPlane<F32>::texel;
-    variance_kernel<F32><<<grid_for(c), 256, 0, s>>>(spatial_args(c, p, 0), c->guide[guide_slot], (const CT *)in, (const MT *)mom,
-                                                     hist, hist_publish, (CT *)out);
+    const SpatialArgs a = spatial_args(c, p, 0);
+    if (a.nt.series)
+        variance_kernel<F32, true><<<grid_for(c), 256, 0, s>>>(a, c->guide[guide_slot], (const CT *)in, (const MT *)mom, hist,
+                                                               hist_publish, (CT *)out);
+    else
+        variance_kernel<F32, false><<<grid_for(c), 256, 0, s>>>(a, c->guide[guide_slot], (const CT *)in, (const MT *)mom, hist,
+                                                                hist_publish, (CT *)out);
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
     return SVGF_OK;
+}
+
+template <bool F32, int STEP, int TERMS>
+svgf_status launch_atrous_tiled(svgf_ctx *c, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out, void *hist_colour,
+                                cudaStream_t s) {
+    using CT = typename ColourPlane<F32>::texel;
+    auto kern = atrous_tiled_kernel<F32, STEP, TERMS>;
+    static bool configured[16] = {};   // per device
+    if (!configured[c->device & 15]) {
+        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileGeom<STEP>::smem_bytes));
+        configured[c->device & 15] = true;
+    }
+    const dim3 grid((c->W + kTileW - 1) / kTileW, ((c->H + kTileRows * STEP - 1) / (kTileRows * STEP)) * STEP);
+    kern<<<grid, kTiledThreads, TileGeom<STEP>::smem_bytes, s>>>(a, c->guide[guide_slot], (const CT *)in, (CT *)out, (CT *)hist_colour);
+    c->launches++;
+    SVGF_CUDA(c, cudaGetLastError());
+    return SVGF_OK;
+}
+
+template <bool F32, int TERMS>
+svgf_status dispatch_atrous_tiled(svgf_ctx *c, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out,
+                                  void *hist_colour, cudaStream_t s) {
+    switch (a.level) {
+        case 0: return launch_atrous_tiled<F32, 1, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 1: return launch_atrous_tiled<F32, 2, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 2: return launch_atrous_tiled<F32, 4, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 3: return launch_atrous_tiled<F32, 8, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 4: return launch_atrous_tiled<F32, 16, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+    }
+    return SVGF_UNSUPPORTED;
 }
 
 template <bool F32>
 svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slot, const void *in, void *out,
                                 void *hist_colour, int level, cudaStream_t s) {
     using CT = typename ColourPlane<F32>::texel;
-    atrous_kernel<F32><<<grid_for(c), 256, 0, s>>>(spatial_args(c, p, level), c->guide[guide_slot], (const CT *)in, (CT *)out,
-                                                   (CT *)hist_colour);
+    const SpatialArgs a = spatial_args(c, p, level);
+    // tiled fast path: levels 0..4, series-mode normal term (phi_normal >= 32), phi_depth > 0 (null texels rely on
+    // |z - inf| * kZ = inf); anything else runs the per-pixel kernel
+    if (level <= 4 && a.nt.series && p->phi_depth > 0.0f && !(p->flags & SVGF_FLAG_BASIC_KERNELS)) {
+        AtrousTiledArgs t;
+        t.W = c->W; t.H = c->H; t.level = level;
+        t.kL_scale = kLog2e / p->phi_colour;
+        t.kZ_scale = kLog2e / ((float)(1 << level) * p->phi_depth);
+        t.k1 = a.nt.k1; t.k2 = a.nt.k2; t.k3 = a.nt.k3; t.k4 = a.nt.k4; t.k5 = a.nt.k5;
+        return (p->phi_normal >= 100.0f) ? dispatch_atrous_tiled<F32, 4>(c, t, guide_slot, in, out, hist_colour, s)
+                                         : dispatch_atrous_tiled<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);
+    }
+    if (a.nt.series)
+        atrous_kernel<F32, true><<<grid_for(c), 256, 0, s>>>(a, c->guide[guide_slot], (const CT *)in, (CT *)out, (CT *)hist_colour);
+    else
+        atrous_kernel<F32, false><<<grid_for(c), 256, 0, s>>>(a, c->guide[guide_slot], (const CT *)in, (CT *)out, (CT *)hist_colour);
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
     return SVGF_OK;

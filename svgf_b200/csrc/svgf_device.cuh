@@ -94,23 +94,51 @@ __device__ __forceinline__ float dot3(float3 a, float3 b) { return (a.x * b.x + 
 
 // ---- edge-stopping weight, reference computeWeight (src/Filter.cuh:407-427):
 //   w = exp(-|dl|/phiL - |dz|/phiZ) * pow(sat(n.n'), phiN)
-// evaluated with one MUFU.LG2 + one MUFU.EX2:
-//   w = 2^( (phiN/4) * lg2(max(sat(d)^4, tiny)) - |dl|*kL - |dz|*kZ )
-// with kL = log2e/phiL, kZ = log2e/phiZ (0 when phiZ == 0, the reference's special case :420) folded per pixel.
-// Two exact-ish squarings before the log keep lg2.approx's absolute error (2^-22.6, which matters because
-// normals of one surface give d = 1 - O(1e-3)) from being multiplied by the full phiN: exponent error is
-// phiN/4 * 2^-22.6 (5e-6 at phiN = 128).  max(.., tiny) keeps d == 0 finite: tiny^(phiN/4) <= 1e-9 for the
-// supported phiN >= 1 (pow(0, phiN) = 0), and phiN == 0 gives 2^0 = 1 like pow(x, 0).
+// evaluated as w = 2^e with one MUFU.EX2.  The normal term needs care: normals of one surface give
+// d = n.n' = 1 - O(1e-3), and pow(d, 128) amplifies any error in log(d) by 128, so
+//   * d itself is formed exactly like the reference: (x*x' + y*y') + z*z' (products of fp16-origin values are
+//     exact in fp32, so FMA contraction cannot change the two roundings);
+//   * for phiN >= 32 ("series" mode) log2(d) = log2(1 - u), u = 1 - sat(d) (exact), is a 5-term Taylor
+//     polynomial with phiN*log2e folded into the coefficients: relative error u^5/6, i.e. < 1e-7 absolute on
+//     every weight that is not itself < 1e-9 (lg2.approx would give 2^-22 ABSOLUTE error on log2 -> 2e-5
+//     relative on the weight);
+//   * for phiN < 32 lg2.approx is accurate enough (error phiN * 2^-22 on the exponent) and exact for d -> 0
+//     (max(d, tiny): tiny^phiN underflows like pow(0, phiN) = 0; phiN == 0 gives 2^0 = 1 like pow(x, 0)).
+// kL = log2e/phiL and kZ = log2e/phiZ (0 when phiZ == 0, the reference's special case :420) are folded per
+// pixel by the callers; `base` = |dl|*kL + |dz|*kZ (+ -log2 of the tap's kernel weight where there is one).
 __device__ __forceinline__ float fast_log2(float x) {  // x is a normal number at every call site
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float edge_weight_log2(float dl_abs_kL, float dz_abs_kZ, float ndot, float phiN_over_4) {
+
+struct NormalTerm {      // uniform per launch
+    float k1, k2, k3, k4, k5;   // series mode: phiN*log2e / i
+    float phiN;
+    int series;
+};
+__host__ __device__ inline NormalTerm make_normal_term(float phiN) {
+    NormalTerm t;
+    const float c = phiN * 1.4426950408889634f;
+    t.k1 = c; t.k2 = c * 0.5f; t.k3 = c * (1.0f / 3.0f); t.k4 = c * 0.25f; t.k5 = c * 0.2f;
+    t.phiN = phiN;
+    t.series = (phiN >= 32.0f) ? 1 : 0;
+    return t;
+}
+// exponent of the weight: e = phiN*log2(sat(ndot)) - base
+template <bool SERIES>
+__device__ __forceinline__ float edge_exponent(float base, float ndot, const NormalTerm &t) {
     const float d = __saturatef(ndot);
-    const float d2 = d * d;
-    const float d4 = fmaxf(d2 * d2, 1e-36f);
-    return phiN_over_4 * fast_log2(d4) - dl_abs_kL - dz_abs_kZ;
+    if (SERIES) {
+        const float u = 1.0f - d;   // exact (d in [0,1]: Sterbenz for d >= 0.5, and exact enough below: weight ~ 0)
+        float p = fmaf(u, t.k5, t.k4);
+        p = fmaf(u, p, t.k3);
+        p = fmaf(u, p, t.k2);
+        p = fmaf(u, p, t.k1);
+        return fmaf(-u, p, -base);
+    } else {
+        return fmaf(t.phiN, fast_log2(fmaxf(d, 1e-37f)), -base);
+    }
 }
 
 __device__ __forceinline__ float fast_exp2(float x) {

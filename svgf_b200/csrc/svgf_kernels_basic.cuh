@@ -102,14 +102,15 @@ temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, const float4 *__res
 
 struct SpatialArgs {
     int W, H;
-    float phi_colour, phi_normal, phi_depth;
+    float phi_colour, phi_depth;
+    NormalTerm nt;
     int step, level;
 };
 
 // ---- variance estimation: reference filter::FilterMoments (src/Filter.cuh:430-525).  Also publishes the
 // history plane (hist_publish, may be null): the caller-visible buffer receives this frame's lengths here so
 // the temporal pass never reads and writes one plane in the same launch (D3).
-template <bool F32>
+template <bool F32, bool SERIES>
 __global__ void __launch_bounds__(256)
 variance_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename ColourPlane<F32>::texel *__restrict__ in,
                 const typename MomentsPlane<F32>::texel *__restrict__ mom, const uint8_t *__restrict__ hist,
@@ -128,6 +129,12 @@ variance_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename 
     const float lc = luminance(cc.x, cc.y, cc.z);
     const float4 gc = __ldg(guide + i);
     const float3 nc = guide_normal(gc);
+    if (nc.x == 0.0f && nc.y == 0.0f && nc.z == 0.0f && a.nt.phiN > 0.0f) {
+        // zero centre normal (background, D7): every weight is exp(..) * pow(0, phiN) = 0, so the sums are 0 and
+        // the output is exactly (0, 0, 0, 0) — same result as running the 49 taps.
+        out[i] = ColourPlane<F32>::encode(make_float4(0.f, 0.f, 0.f, 0.f));
+        return;
+    }
     const float kL = kLog2e / a.phi_colour;                                    // :460
     const float phiZ0 = fmaxf(gc.y, 1e-8f) * 3.0f * a.phi_depth;              // :461
     float sw = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sm1 = 0.f, sm2 = 0.f;
@@ -144,7 +151,7 @@ variance_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename 
             const float lq = luminance(cq.x, cq.y, cq.z);
             const float phiZ = phiZ0 * sqrtf((float)(xx * xx + yy * yy));      // :488
             const float kZ = (phiZ == 0.0f) ? 0.0f : kLog2e / phiZ;            // :420
-            const float e = edge_weight_log2(fabsf(lc - lq) * kL, fabsf(gc.x - gq.x) * kZ, dot3(nc, guide_normal(gq)), 0.25f * a.phi_normal);
+            const float e = edge_exponent<SERIES>(fmaf(fabsf(gc.x - gq.x), kZ, fabsf(lc - lq) * kL), dot3(nc, guide_normal(gq)), a.nt);
             const float w = fast_exp2(e);
             sw += w;                                                           // :497-499
             sr += cq.x * w; sg += cq.y * w; sb += cq.z * w;
@@ -160,7 +167,7 @@ variance_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename 
 }
 
 // ---- one a-trous level: reference filter::FilterKernel (src/Filter.cuh:527-624) ---------------------------
-template <bool F32>
+template <bool F32, bool SERIES>
 __global__ void __launch_bounds__(256)
 atrous_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename ColourPlane<F32>::texel *__restrict__ in,
               typename ColourPlane<F32>::texel *__restrict__ out, typename ColourPlane<F32>::texel *__restrict__ hist_colour) {
@@ -194,7 +201,7 @@ atrous_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename Co
             const float4 gq = __ldg(guide + qi);
             const float lq = luminance(cq.x, cq.y, cq.z);
             const float kZ = kZ1 / sqrtf((float)(xx * xx + yy * yy));          // phiZ * length(xx,yy), :595
-            const float e = edge_weight_log2(fabsf(lc - lq) * kL, fabsf(gc.x - gq.x) * kZ, dot3(nc, guide_normal(gq)), 0.25f * a.phi_normal);
+            const float e = edge_exponent<SERIES>(fmaf(fabsf(gc.x - gq.x), kZ, fabsf(lc - lq) * kL), dot3(nc, guide_normal(gq)), a.nt);
             const float w = fast_exp2(e) * (KW[xx < 0 ? -xx : xx] * KW[yy < 0 ? -yy : yy]);  // :604
             sw += w;                                                           // :607-608
             sr += w * cq.x; sg += w * cq.y; sb += w * cq.z;

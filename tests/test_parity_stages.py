@@ -6,9 +6,9 @@ import numpy as np
 import pytest
 import torch
 
-from common import assert_close, random_scene
+from common import F32_FLOOR_RADIANCE, F32_REL_TOL, assert_close, random_scene, rel_err
 from gpu_util import load_state_from_oracle, npy
-from oracle_lib import OracleFilter
+from oracle_lib import OracleFilter, oracle
 from svgf_b200 import SvgfFilter, _lib
 
 pytestmark = pytest.mark.gpu
@@ -64,21 +64,69 @@ def test_variance(size, storage):
     of.HistoryLengthBuffer[...] = rng.integers(1, 8, size=(H, W)).astype(np.uint8)
     f.HistoryLengthBuffer.copy_(torch.from_numpy(of.HistoryLengthBuffer))
     of.FilterMoments(); f.FilterMoments()
-    assert_close(npy(f.FilterBuffer[0]), of.FilterBuffer[0], storage, f"variance {size}")
+    got, want = npy(f.FilterBuffer[0]), of.FilterBuffer[0]
+    if storage == "f32":
+        # variance = (M2 - M1^2) * 4/h cancels: with these random moments M2 ~ 0.5 and 4/h up to 4, one fp32 ulp
+        # of M2 is 2.4e-7 of variance; relative error is taken against max(|var|, 0.05)
+        assert rel_err(got[..., :3], want[..., :3], F32_FLOOR_RADIANCE) <= F32_REL_TOL
+        assert rel_err(got[..., 3], want[..., 3], 5e-2) <= F32_REL_TOL
+    else:
+        # fp16 variance values near the cancellation point flip more often; bound the size of the flips
+        assert_close(got, want, storage, f"variance {size}", max_flips=0.10)
+
+
+def _atrous_inputs(of, f, rng, smooth):
+    H, W = of.Height, of.Width
+    cdt = of.FilterBuffer[0].dtype
+    if smooth:
+        # smooth shading + noise whose variance channel is consistent with the noise (what the filter is for)
+        yy, xx = np.mgrid[0:H, 0:W]
+        base = 0.45 + 0.3 * np.sin(xx / 17.0)[..., None] * np.cos(yy / 11.0)[..., None] * np.array([1.0, 0.8, 0.6])
+        sigma = 0.05
+        start = np.empty((H, W, 4), np.float64)
+        start[..., :3] = base + rng.normal(scale=sigma, size=(H, W, 3))
+        start[..., 3] = sigma * sigma * rng.uniform(0.5, 1.5, size=(H, W))
+        start = start.astype(cdt)
+    else:
+        start = rng.uniform(0, 1.1, size=(H, W, 4)).astype(cdt)      # white noise, some > 1 (clamp)
+        start[..., 3] = (rng.uniform(0, 0.05, size=(H, W)) * (rng.uniform(size=(H, W)) < 0.8)).astype(cdt)  # 20 % exact zeros
+    of.FilterBuffer[0][...] = start
+    f.FilterBuffer[0].copy_(torch.from_numpy(start))
 
 
 @pytest.mark.parametrize("storage", ["f16", "f32"])
 @pytest.mark.parametrize("size", SIZES)
-@pytest.mark.parametrize("levels", [1, 2, 5])
-def test_atrous(size, storage, levels):
+@pytest.mark.parametrize("level", [0, 1, 2, 3, 4])
+def test_atrous_single_level(size, storage, level):
+    # every level on its own from identical inputs (white-noise colours, 20 % zero variances: the worst case for
+    # the edge-stopping functions): this is the kernel's own error, nothing to amplify it
+    W, H = size
+    of, f = make_pair(W, H, storage, seed=W * 13 + H + level)
+    _atrous_inputs(of, f, np.random.default_rng(9 + level), smooth=False)
+    P = of.PingPongInx
+    g = of.gbuf(P)
+    out = np.zeros_like(of.FilterBuffer[0])
+    hc = of.RenderBuffer[P].copy()
+    assert oracle().svgf_oracle_atrous_level(C.byref(of.params), W, H, of.storage, C.byref(g), of.FilterBuffer[0].ctypes.data,
+                                             out.ctypes.data, hc.ctypes.data, level) == 0
+    res = C.c_void_p()
+    gs = f.Framebuffer[P].as_struct()
+    st = f.lib.svgf_atrous(f._ctx, C.byref(f.params), C.byref(gs), C.c_void_p(f.FilterBuffer[0].data_ptr()),
+                           C.c_void_p(f.FilterBuffer[1].data_ptr()), C.c_void_p(f.RenderBuffer[P].data_ptr()), level, 1,
+                           C.byref(res), f._stream())
+    assert st == 0 and res.value == f.FilterBuffer[1].data_ptr()
+    assert_close(npy(f.FilterBuffer[1]), out, storage, f"a-trous level {level} {size}")
+    assert_close(npy(f.RenderBuffer[P]), hc, storage, f"colour history after level {level} {size}")
+
+
+@pytest.mark.parametrize("storage", ["f16", "f32"])
+@pytest.mark.parametrize("size", SIZES[2:])
+@pytest.mark.parametrize("levels", [2, 5])
+def test_atrous_cascade(size, storage, levels):
+    # the full cascade through one svgf_atrous call on well-conditioned content
     W, H = size
     of, f = make_pair(W, H, storage, seed=W * 13 + H + levels)
-    cdt = of.FilterBuffer[0].dtype
-    rng = np.random.default_rng(9)
-    start = rng.uniform(0, 1.1, size=(H, W, 4)).astype(cdt)
-    start[..., 3] = (rng.uniform(0, 0.05, size=(H, W)) * (rng.uniform(size=(H, W)) < 0.8)).astype(cdt)  # 20 % exact zeros
-    of.FilterBuffer[0][...] = start
-    f.FilterBuffer[0].copy_(torch.from_numpy(start))
+    _atrous_inputs(of, f, np.random.default_rng(21), smooth=True)
     of.params.atrous_iterations = f.params.atrous_iterations = levels
     of.WaveletFilter(); f.WaveletFilter()
     P = of.PingPongInx

@@ -158,6 +158,9 @@ def test_pan_sequence_matches_reference_where_the_history_race_is_benign():
         inside = (qx >= 0) & (qx < W) & (qy >= 0) & (qy < H)
         qxc, qyc = np.clip(qx, 0, W - 1), np.clip(qy, 0, H - 1)
         benign = ~inside | (h_before[qyc, qxc] == o.HistoryLengthBuffer[qyc, qxc])
+        # a pixel whose reprojection FAILS never looks at the history it read: after the reset frame every
+        # stored length is >= 1, so a new length of 1 can only come from a failed reprojection
+        benign |= (o.HistoryLengthBuffer == 1) if t >= 1 else np.ones((H, W), bool)
         got_h = r.get_plane(PLANE_HISTORY, 0)
         assert np.array_equal(got_h[benign], o.HistoryLengthBuffer[benign]), f"frame {t}"
         got_c = r.get_plane(PLANE_RENDER, P)
@@ -166,4 +169,45 @@ def test_pan_sequence_matches_reference_where_the_history_race_is_benign():
         compared += int(benign.sum())
         o.FilterMoments(); o.WaveletFilter(); o.EndFrame()
     assert compared > 0.5 * 6 * W * H
+    r.close()
+
+
+def test_free_running_drift_is_no_worse_than_the_reference_kernels_own():
+    # Yardstick for free-running parity in the reference's fp16 layout: run (a) the reference's own kernels and
+    # (b) the new CUDA path free-running (each feeding on its own outputs) next to the free-running oracle on a
+    # static-camera sequence (no motion => the reference is deterministic, D3).  Wherever the accumulated
+    # variance is ~0 the reference math amplifies one-ulp differences, so BOTH drift from the oracle; the new
+    # path must not drift more than the reference's own kernels do (x2 + a small floor for sampling noise).
+    import torch
+    from common import F16_ABS_FLOOR, F16_MAX_ULPS, half_ulp_diff
+    from gpu_util import npy, upload_inputs
+    from svgf_b200 import SvgfFilter
+    W, H, frames = 384, 216, 16
+    o = OracleFilter(W, H, storage="f16")
+    o.params.mesh_id_mode = _lib.SVGF_MESH_ID_REFERENCE_VACUOUS
+    f = SvgfFilter(W, H, storage="f16")
+    f.params.mesh_id_mode = _lib.SVGF_MESH_ID_REFERENCE_VACUOUS
+    rp = RefParams.from_svgf(o.params, moments_quirk=0)
+    r = RefKernels(W, H)
+    o.Reset(); f.Reset()
+    worst = {"ref": {"flips": 0.0, "outliers": 0.0}, "ours": {"flips": 0.0, "outliers": 0.0}}
+    for t in range(frames):
+        planes = synth.frame_host(W, H, t, pan_px=0.0, vert_px=0.0)
+        o.set_inputs(planes); upload_inputs(f, planes)
+        P = o.PingPongInx
+        r.set_gbuffer(P, planes["normal"], planes["uv"], planes["motion"])
+        r.set_plane(PLANE_RENDER, P, planes["colour"])
+        o.Filter(); f.Filter()
+        assert ref().svgf_ref_frame(r.ctx, rp, 1) == 0
+        assert np.array_equal(r.get_plane(PLANE_HISTORY, 0), o.HistoryLengthBuffer)
+        assert np.array_equal(npy(f.HistoryLengthBuffer), o.HistoryLengthBuffer)
+        for who, got in (("ref", r.get_plane(PLANE_FILTER, 0)), ("ours", npy(f.FilterBuffer[0]))):
+            u = half_ulp_diff(got, o.FilterBuffer[0])
+            absd = np.abs(got.astype(np.float64) - o.FilterBuffer[0].astype(np.float64))
+            worst[who]["flips"] = max(worst[who]["flips"], float((u > 0).mean()))
+            worst[who]["outliers"] = max(worst[who]["outliers"], float(((u > F16_MAX_ULPS) & (absd > F16_ABS_FLOOR)).mean()))
+        o.EndFrame(); f.EndFrame()
+    print(f"\n[free-running drift vs oracle, fp16, {W}x{H} x{frames}] {worst}")
+    assert worst["ours"]["flips"] <= 2 * worst["ref"]["flips"] + 2e-3
+    assert worst["ours"]["outliers"] <= 2 * worst["ref"]["outliers"] + 2e-4
     r.close()
