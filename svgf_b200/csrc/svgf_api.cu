@@ -10,6 +10,8 @@
 #include "../../include/svgf.h"
 #include "svgf_kernels_basic.cuh"
 #include "svgf_kernels_tiled.cuh"
+#include "svgf_kernels_packed.cuh"
+#include <cstdlib>
 
 using namespace svgf;
 
@@ -17,7 +19,10 @@ struct svgf_ctx {
     int device = 0, W = 0, H = 0;
     svgf_storage storage = SVGF_STORE_F16;
     uint8_t *hist_shadow = nullptr;       // this frame's history lengths until published (D3)
-    float4 *guide[2] = {nullptr, nullptr};  // compact guide planes, ping-pong
+    Guide guide[2] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // compact guide planes, ping-pong
+    int num_sms = 148;
+    unsigned int *worklist = nullptr;     // indices of short-history pixels queued by the fused temporal pass
+    unsigned int *work_counter = nullptr;
     const void *guide_key[2] = {nullptr, nullptr};  // motion_depth pointer of the G-buffer each plane was built from
     int guide_cur = 0;                    // slot of the most recently built guide
     bool force_fail_next = false;         // set by svgf_reset
@@ -118,9 +123,15 @@ svgf_status ensure_guide(svgf_ctx *c, const svgf_gbuffer *g, cudaStream_t s, int
 template <bool F32>
 svgf_status launch_temporal(svgf_ctx *c, const svgf_params *p, const svgf_gbuffer *cur, const svgf_gbuffer *prev,
                             const void *prev_colour, void *cur_colour, const uint8_t *hist_prev, uint8_t *hist_out,
-                            void *cur_mom, const void *prev_mom, cudaStream_t s) {
+                            void *cur_mom, const void *prev_mom, void *fused_var_out, cudaStream_t s) {
     using CT = typename ColourPlane<F32>::texel;
     using MT = typename MomentsPlane<F32>::texel;
+    TemporalFused<F32> fused;
+    fused.var_out = (CT *)fused_var_out;
+    fused.worklist = c->worklist;
+    fused.counter = c->work_counter;
+    fused.zero_normal_shortcut = p->phi_normal > 0.0f;
+    if (fused_var_out) SVGF_CUDA(c, cudaMemsetAsync(c->work_counter, 0, sizeof(unsigned int), s));
     TemporalArgs a;
     a.W = c->W; a.H = c->H;
     a.depth_threshold = p->depth_threshold; a.normal_threshold = p->normal_threshold;
@@ -139,11 +150,11 @@ svgf_status launch_temporal(svgf_ctx *c, const svgf_params *p, const svgf_gbuffe
     if (prev_slot >= 0)
         temporal_kernel<F32, true><<<grid, 256, 0, s>>>(a, view(c, cur), view(c, prev), c->guide[prev_slot], c->guide[cur_slot],
                                                         (const CT *)prev_colour, (CT *)cur_colour, hist_prev, hist_out,
-                                                        (MT *)cur_mom, (const MT *)prev_mom);
+                                                        (MT *)cur_mom, (const MT *)prev_mom, fused);
     else
-        temporal_kernel<F32, false><<<grid, 256, 0, s>>>(a, view(c, cur), view(c, prev), nullptr, c->guide[cur_slot],
+        temporal_kernel<F32, false><<<grid, 256, 0, s>>>(a, view(c, cur), view(c, prev), Guide{nullptr, nullptr, nullptr}, c->guide[cur_slot],
                                                          (const CT *)prev_colour, (CT *)cur_colour, hist_prev, hist_out,
-                                                         (MT *)cur_mom, (const MT *)prev_mom);
+                                                         (MT *)cur_mom, (const MT *)prev_mom, fused);
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
     c->guide_key[cur_slot] = cur->motion_depth;
@@ -178,32 +189,92 @@ svgf_status launch_variance(svgf_ctx *c, const svgf_params *p, int guide_slot, c
     return SVGF_OK;
 }
 
-template <bool F32, int STEP, int TERMS>
-svgf_status launch_atrous_tiled(svgf_ctx *c, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out, void *hist_colour,
-                                cudaStream_t s) {
+template <bool F32>
+svgf_status launch_variance_sparse(svgf_ctx *c, const svgf_params *p, int guide_slot, const void *in, const void *mom,
+                                   const uint8_t *hist, void *out, cudaStream_t s) {
     using CT = typename ColourPlane<F32>::texel;
-    auto kern = atrous_tiled_kernel<F32, STEP, TERMS>;
-    static bool configured[16] = {};   // per device
-    if (!configured[c->device & 15]) {
-        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileGeom<STEP>::smem_bytes));
-        configured[c->device & 15] = true;
-    }
-    const dim3 grid((c->W + kTileW - 1) / kTileW, ((c->H + kTileRows * STEP - 1) / (kTileRows * STEP)) * STEP);
-    kern<<<grid, kTiledThreads, TileGeom<STEP>::smem_bytes, s>>>(a, c->guide[guide_slot], (const CT *)in, (CT *)out, (CT *)hist_colour);
+    using MT = typename MomentsPlane<F32>::texel;
+    const SpatialArgs a = spatial_args(c, p, 0);
+    const int grid = c->num_sms * 8;
+    if (a.nt.series)
+        variance_sparse_kernel<F32, true><<<grid, 256, 0, s>>>(a, c->guide[guide_slot], (const CT *)in, (const MT *)mom, hist,
+                                                               c->worklist, c->work_counter, (CT *)out);
+    else
+        variance_sparse_kernel<F32, false><<<grid, 256, 0, s>>>(a, c->guide[guide_slot], (const CT *)in, (const MT *)mom, hist,
+                                                                c->worklist, c->work_counter, (CT *)out);
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
     return SVGF_OK;
 }
 
+template <bool F32, int STEP, int RG, int TERMS>
+svgf_status launch_atrous_tiled(svgf_ctx *c, AtrousTiledArgs a, int guide_slot, const void *in, void *out, void *hist_colour,
+                                cudaStream_t s) {
+    using CT = typename ColourPlane<F32>::texel;
+    using G = TileGeom<F32, STEP, RG>;
+    auto kern = atrous_tiled_kernel<F32, STEP, RG, TERMS>;
+    static int ctas_per_sm[16] = {};   // per device, 0 = not configured yet
+    int &cps = ctas_per_sm[c->device & 15];
+    if (cps == 0) {
+        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
+        int n = 0;
+        SVGF_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, G::threads, G::smem_bytes));
+        if (n < 1) return SVGF_UNSUPPORTED;
+        cps = n;
+    }
+    a.tiles_x = (c->W + kTileW - 1) / kTileW;
+    a.tiles_y = ((c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP)) * STEP;
+    const int n_tiles = a.tiles_x * a.tiles_y;
+    const int grid = n_tiles < c->num_sms * cps ? n_tiles : c->num_sms * cps;
+    kern<<<grid, G::threads, G::smem_bytes, s>>>(a, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in, (CT *)out,
+                                                 (CT *)hist_colour);
+    c->launches++;
+    SVGF_CUDA(c, cudaGetLastError());
+    return SVGF_OK;
+}
+
+template <bool F32, int STEP, int TERMS>
+svgf_status launch_atrous_packed(svgf_ctx *c, AtrousTiledArgs a, int guide_slot, const void *in, void *out, void *hist_colour,
+                                 cudaStream_t s) {
+    using CT = typename ColourPlane<F32>::texel;
+    using G = PackedGeom<STEP>;
+    auto kern = atrous_packed_kernel<F32, STEP, TERMS>;
+    static bool configured[16] = {};
+    if (!configured[c->device & 15]) {
+        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
+        configured[c->device & 15] = true;
+    }
+    const dim3 grid((c->W + kTileW - 1) / kTileW, ((c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP)) * STEP);
+    kern<<<grid, kPkThreads, G::smem_bytes, s>>>(a, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in, (CT *)out,
+                                                 (CT *)hist_colour);
+    c->launches++;
+    SVGF_CUDA(c, cudaGetLastError());
+    return SVGF_OK;
+}
+template <bool F32, int TERMS>
+svgf_status dispatch_atrous_packed(svgf_ctx *c, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out,
+                                   void *hist_colour, cudaStream_t s) {
+    switch (a.level) {
+        case 0: return launch_atrous_packed<F32, 1, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 1: return launch_atrous_packed<F32, 2, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 2: return launch_atrous_packed<F32, 4, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 3: return launch_atrous_packed<F32, 8, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 4: return launch_atrous_packed<F32, 16, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+    }
+    return SVGF_UNSUPPORTED;
+}
+
+// Row groups per CTA: 2 (256 threads, two CTAs per SM) while the tile fits twice; 4 (512 threads, one CTA per SM,
+// less vertical halo) for the wide-halo levels — chosen so every instantiation fits the 227 KB of shared memory.
 template <bool F32, int TERMS>
 svgf_status dispatch_atrous_tiled(svgf_ctx *c, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out,
                                   void *hist_colour, cudaStream_t s) {
     switch (a.level) {
-        case 0: return launch_atrous_tiled<F32, 1, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 1: return launch_atrous_tiled<F32, 2, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 2: return launch_atrous_tiled<F32, 4, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 3: return launch_atrous_tiled<F32, 8, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 4: return launch_atrous_tiled<F32, 16, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 0: return launch_atrous_tiled<F32, 1, 2, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 1: return launch_atrous_tiled<F32, 2, 2, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 2: return launch_atrous_tiled<F32, 4, 2, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 3: return launch_atrous_tiled<F32, 8, 4, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 4: return launch_atrous_tiled<F32, 16, (F32 ? 2 : 4), TERMS>(c, a, guide_slot, in, out, hist_colour, s);
     }
     return SVGF_UNSUPPORTED;
 }
@@ -215,12 +286,21 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
     const SpatialArgs a = spatial_args(c, p, level);
     // tiled fast path: levels 0..4, series-mode normal term (phi_normal >= 32), phi_depth > 0 (null texels rely on
     // |z - inf| * kZ = inf); anything else runs the per-pixel kernel
-    if (level <= 4 && a.nt.series && p->phi_depth > 0.0f && !(p->flags & SVGF_FLAG_BASIC_KERNELS)) {
+    // (the bulk copies need 16-byte-aligned row segments: even width for the 8-byte fp16 texels)
+    if (level <= 4 && a.nt.series && p->phi_depth > 0.0f && !(p->flags & SVGF_FLAG_BASIC_KERNELS) && (F32 || c->W % 2 == 0) &&
+        ((uintptr_t)in % 16) == 0) {
         AtrousTiledArgs t;
-        t.W = c->W; t.H = c->H; t.level = level;
+        t.W = c->W; t.H = c->H; t.level = level; t.tiles_x = t.tiles_y = 0;
         t.kL_scale = kLog2e / p->phi_colour;
         t.kZ_scale = kLog2e / ((float)(1 << level) * p->phi_depth);
         t.k1 = a.nt.k1; t.k2 = a.nt.k2; t.k3 = a.nt.k3; t.k4 = a.nt.k4; t.k5 = a.nt.k5;
+        // default: packed FP32x2 kernel (needs an even width and 16-byte-aligned planes for its pair loads/stores);
+        // SVGF_ATROUS_VARIANT=bulk selects the persistent bulk-copy (UBLKCP) scalar kernel for A/B measurements
+        static const char *variant = getenv("SVGF_ATROUS_VARIANT");
+        const bool want_bulk = variant && !strcmp(variant, "bulk");
+        if (!want_bulk && c->W % 2 == 0 && ((uintptr_t)out % 16) == 0 && (!hist_colour || ((uintptr_t)hist_colour % 16) == 0))
+            return (p->phi_normal >= 100.0f) ? dispatch_atrous_packed<F32, 4>(c, t, guide_slot, in, out, hist_colour, s)
+                                             : dispatch_atrous_packed<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);
         return (p->phi_normal >= 100.0f) ? dispatch_atrous_tiled<F32, 4>(c, t, guide_slot, in, out, hist_colour, s)
                                          : dispatch_atrous_tiled<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);
     }
@@ -301,7 +381,14 @@ svgf_status svgf_create(svgf_ctx **out, int device, int width, int height, svgf_
     c->device = device; c->W = width; c->H = height; c->storage = storage;
     const size_t n = (size_t)width * height;
     cudaError_t e = cudaMalloc(&c->hist_shadow, n);
-    for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaMalloc(&c->guide[k], n * sizeof(float4));
+    for (int k = 0; k < 2 && e == cudaSuccess; k++) {
+        e = cudaMalloc(&c->guide[k].n, n * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMalloc(&c->guide[k].dz, n * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&c->guide[k].mid, n * sizeof(unsigned short));
+    }
+    c->num_sms = prop.multiProcessorCount;
+    if (e == cudaSuccess) e = cudaMalloc(&c->worklist, n * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->work_counter, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(c->hist_shadow, 0, n);
     if (e != cudaSuccess) { svgf_destroy(c); return SVGF_CUDA_ERROR; }
     *out = c;
@@ -312,7 +399,9 @@ void svgf_destroy(svgf_ctx *c) {
     if (!c) return;
     DeviceGuard guard(c->device);
     cudaFree(c->hist_shadow);
-    for (int k = 0; k < 2; k++) cudaFree(c->guide[k]);
+    cudaFree(c->worklist);
+    cudaFree(c->work_counter);
+    for (int k = 0; k < 2; k++) { cudaFree(c->guide[k].n); cudaFree(c->guide[k].dz); cudaFree(c->guide[k].mid); }
     if (c->prof_ev) {
         for (int i = 0; i < svgf_ctx::kMaxProf * 4; i++) cudaEventDestroy(c->prof_ev[i]);
         delete[] c->prof_ev;
@@ -365,8 +454,8 @@ svgf_status svgf_temporal(svgf_ctx *c, const svgf_params *p, const svgf_gbuffer 
     if (!guard.ok) return SVGF_CUDA_ERROR;
     cudaStream_t s = (cudaStream_t)stream;
     st = (c->storage == SVGF_STORE_F32)
-             ? launch_temporal<true>(c, p, cur, prev, prev_colour, cur_colour, history, c->hist_shadow, cur_moments, prev_moments, s)
-             : launch_temporal<false>(c, p, cur, prev, prev_colour, cur_colour, history, c->hist_shadow, cur_moments, prev_moments, s);
+             ? launch_temporal<true>(c, p, cur, prev, prev_colour, cur_colour, history, c->hist_shadow, cur_moments, prev_moments, nullptr, s)
+             : launch_temporal<false>(c, p, cur, prev, prev_colour, cur_colour, history, c->hist_shadow, cur_moments, prev_moments, nullptr, s);
     if (st) return st;
     // publish: the caller-visible plane now holds this frame's lengths
     SVGF_CUDA(c, cudaMemcpyAsync(history, c->hist_shadow, (size_t)c->W * c->H, cudaMemcpyDeviceToDevice, s));
@@ -423,22 +512,32 @@ svgf_status svgf_frame(svgf_ctx *c, const svgf_params *p, const svgf_gbuffer gbu
     cudaStream_t s = (cudaStream_t)stream;
     const bool f32 = (c->storage == SVGF_STORE_F32);
 
-    prof_mark(c, 0, s);
-    // temporal: reads the caller-visible history plane (previous frame), writes the shadow plane
-    st = f32 ? launch_temporal<true>(c, p, &gbuf[P], &gbuf[Q], b->render[Q], b->render[P], b->history, c->hist_shadow,
-                                     b->moments[P], b->moments[Q], s)
-             : launch_temporal<false>(c, p, &gbuf[P], &gbuf[Q], b->render[Q], b->render[P], b->history, c->hist_shadow,
-                                      b->moments[P], b->moments[Q], s);
-    if (st) return st;
-    prof_mark(c, 1, s);
-    // variance -> filter[N & 1] so that N ping-pong levels end in filter[0] (the reference copies instead,
-    // src/App.cu:510-513); it also publishes the history plane.
     const int N = p->atrous_iterations;
     void *v_out = b->filter[N & 1], *other = b->filter[1 - (N & 1)];
-    const int slot = c->guide_cur;
-    st = f32 ? launch_variance<true>(c, p, slot, b->render[P], b->moments[P], c->hist_shadow, b->history, v_out, s)
-             : launch_variance<false>(c, p, slot, b->render[P], b->moments[P], c->hist_shadow, b->history, v_out, s);
+    const bool basic = (p->flags & SVGF_FLAG_BASIC_KERNELS) != 0;
+    prof_mark(c, 0, s);
+    // temporal: reads the caller-visible history plane (previous frame), writes the shadow plane.  Fused form: it
+    // also writes the variance pass's output for every pixel that pass only copies or zeroes and queues the
+    // short-history pixels; -> filter[N & 1] so that N ping-pong levels end in filter[0] (the reference copies
+    // instead, src/App.cu:510-513).
+    st = f32 ? launch_temporal<true>(c, p, &gbuf[P], &gbuf[Q], b->render[Q], b->render[P], b->history, c->hist_shadow,
+                                     b->moments[P], b->moments[Q], basic ? nullptr : v_out, s)
+             : launch_temporal<false>(c, p, &gbuf[P], &gbuf[Q], b->render[Q], b->render[P], b->history, c->hist_shadow,
+                                      b->moments[P], b->moments[Q], basic ? nullptr : v_out, s);
     if (st) return st;
+    prof_mark(c, 1, s);
+    const int slot = c->guide_cur;
+    if (basic) {
+        st = f32 ? launch_variance<true>(c, p, slot, b->render[P], b->moments[P], c->hist_shadow, b->history, v_out, s)
+                 : launch_variance<false>(c, p, slot, b->render[P], b->moments[P], c->hist_shadow, b->history, v_out, s);
+        if (st) return st;
+    } else {
+        // 7x7 estimate for the queued pixels only, then publish this frame's history lengths
+        st = f32 ? launch_variance_sparse<true>(c, p, slot, b->render[P], b->moments[P], c->hist_shadow, v_out, s)
+                 : launch_variance_sparse<false>(c, p, slot, b->render[P], b->moments[P], c->hist_shadow, v_out, s);
+        if (st) return st;
+        SVGF_CUDA(c, cudaMemcpyAsync(b->history, c->hist_shadow, (size_t)c->W * c->H, cudaMemcpyDeviceToDevice, s));
+    }
     prof_mark(c, 2, s);
     void *result = nullptr;
     st = run_atrous(c, p, slot, v_out, other, b->render[P], 0, N, &result, s);

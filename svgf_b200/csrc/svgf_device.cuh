@@ -65,31 +65,36 @@ __device__ __forceinline__ float mix_rn(float x, float y, float a) {
     return __fadd_rn(__fmul_rn(x, __fsub_rn(1.0f, a)), __fmul_rn(y, a));
 }
 
-// ---- compact guide texel (16 B): everything the consistency tests and edge-stopping functions need from
-// the three G-buffer planes (motion.zw, normal.xyz, uv.w = 32 B of texels), emitted once per frame by the
-// temporal pass.  Exact: depth stays fp32, normals are already fp16 in the G-buffer, the mesh id keeps its
-// fp16 bits.
-//   x: z  (GetDepth: 0 -> 1e30, src/Filter.cuh:199-207)   y: dz (0 for background)
-//   z: half2(nx, ny) bits                                  w: lo16 = half(nz) bits, hi16 = uv.w bits
-__device__ __forceinline__ float4 make_guide(float4 motion, ushort4 nrm, ushort4 uv) {
-    float4 g;
+// ---- compact guide planes: everything the consistency tests and edge-stopping functions need from the three
+// G-buffer planes (motion.zw, normal.xyz, uv.w = 32 B of texels), emitted once per frame by the temporal pass
+// and kept by the context for the next frame's previous-frame tests.  Exact: depth stays fp32, the fp16
+// normals are widened to fp32 (so the a-trous tiles can be bulk-copied into shared memory with no per-texel
+// conversion), the mesh id keeps its fp16 bits.
+//   n   : float4 (z', nx, ny, nz)   z' = GetDepth: 0 -> 1e30 (src/Filter.cuh:199-207)      16 B/px
+//   dz  : float  depth derivative (0 for background)                                         4 B/px
+//   mid : fp16 bits of uv.w, the instance index (GBuffer.frag:77)                            2 B/px
+struct Guide {
+    float4 *n;
+    float *dz;
+    unsigned short *mid;
+};
+struct GuideTexel {
+    float4 n;
+    float dz;
+    unsigned short mid;
+};
+__device__ __forceinline__ GuideTexel make_guide(float4 motion, ushort4 nrm, ushort4 uv) {
+    GuideTexel g;
     const bool bg = (motion.z == 0.0f);
-    g.x = bg ? kBackgroundZ : motion.z;
-    g.y = bg ? 0.0f : motion.w;
-    g.z = __uint_as_float((uint32_t)nrm.x | ((uint32_t)nrm.y << 16));
-    g.w = __uint_as_float((uint32_t)nrm.z | ((uint32_t)uv.w << 16));
+    g.n = make_float4(bg ? kBackgroundZ : motion.z, __half2float(__ushort_as_half(nrm.x)), __half2float(__ushort_as_half(nrm.y)),
+                      __half2float(__ushort_as_half(nrm.z)));
+    g.dz = bg ? 0.0f : motion.w;
+    g.mid = uv.w;
     return g;
 }
-__device__ __forceinline__ float3 guide_normal(float4 g) {
-    const uint32_t a = __float_as_uint(g.z), b = __float_as_uint(g.w);
-    const float2 xy = __half22float2(*reinterpret_cast<const __half2 *>(&a));
-    const float z = __half2float(__ushort_as_half((unsigned short)(b & 0xffffu)));
-    return make_float3(xy.x, xy.y, z);
-}
+__device__ __forceinline__ float3 guide_normal(float4 gn) { return make_float3(gn.y, gn.z, gn.w); }
 // int(SampleCuTexture(UV).w) as GBuffer.frag:77 intended it: fp16 -> float -> int (cvt.rzi)
-__device__ __forceinline__ int guide_mesh_id(float4 g) {
-    return __float2int_rz(__half2float(__ushort_as_half((unsigned short)(__float_as_uint(g.w) >> 16))));
-}
+__device__ __forceinline__ int guide_mesh_id(unsigned short bits) { return __float2int_rz(__half2float(__ushort_as_half(bits))); }
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 
 // ---- edge-stopping weight, reference computeWeight (src/Filter.cuh:407-427):

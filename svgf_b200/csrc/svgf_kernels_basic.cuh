@@ -20,6 +20,17 @@ struct GBufView {  // pitch-linear G-buffer planes (include/svgf.h svgf_gbuffer)
     }
 };
 
+// Fused-frame outputs of the temporal pass (svgf_frame): besides RenderBuffer[P] it also produces the variance
+// pass's output for every pixel that pass would merely copy (history >= 4, reference src/Filter.cuh:518-523) or
+// zero (zero centre normal: all 49 weights are pow(0, phiN) = 0), and queues the remaining short-history pixels
+// for the sparse 7x7 kernel.  var_out == nullptr disables all of it (stand-alone svgf_temporal).
+template <bool F32> struct TemporalFused {
+    typename ColourPlane<F32>::texel *var_out;
+    unsigned int *worklist;
+    unsigned int *counter;
+    int zero_normal_shortcut;   // phi_normal > 0
+};
+
 struct TemporalArgs {
     int W, H;
     float depth_threshold, normal_threshold;
@@ -31,10 +42,12 @@ struct TemporalArgs {
 
 // ---- build the compact guide plane from a G-buffer (used when a stage is called on a G-buffer the temporal
 // pass has not seen) ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) build_guide_kernel(GBufView g, float4 *__restrict__ guide, int W, int H) {
+__global__ void __launch_bounds__(256) build_guide_kernel(GBufView g, Guide guide, int W, int H) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= W || y >= H) return;
-    guide[(size_t)y * W + x] = make_guide(g.mot(x, y), g.nrm(x, y), g.uvw(x, y));
+    const GuideTexel t = make_guide(g.mot(x, y), g.nrm(x, y), g.uvw(x, y));
+    const size_t i = (size_t)y * W + x;
+    guide.n[i] = t.n; guide.dz[i] = t.dz; guide.mid[i] = t.mid;
 }
 
 // ---- temporal reprojection + accumulation: reference filter::TemporalFilter (src/Filter.cuh:359-404) with
@@ -42,18 +55,19 @@ __global__ void __launch_bounds__(256) build_guide_kernel(GBufView g, float4 *__
 // plane cached by the previous frame instead of the three previous G-buffer planes.
 template <bool F32, bool PREV_GUIDE>
 __global__ void __launch_bounds__(256)
-temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, const float4 *__restrict__ prev_guide,
-                float4 *__restrict__ cur_guide, const typename ColourPlane<F32>::texel *__restrict__ prev_colour,
+temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, Guide prev_guide, Guide cur_guide, const typename ColourPlane<F32>::texel *__restrict__ prev_colour,
                 typename ColourPlane<F32>::texel *colour, const uint8_t *__restrict__ hist_prev, uint8_t *__restrict__ hist_out,
                 typename MomentsPlane<F32>::texel *__restrict__ cur_mom,
-                const typename MomentsPlane<F32>::texel *__restrict__ prev_mom) {
+                const typename MomentsPlane<F32>::texel *__restrict__ prev_mom, TemporalFused<F32> fused) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= a.W || y >= a.H) return;
+    const bool inb = (x < a.W && y < a.H);
+    bool queue = false;
     const size_t i = (size_t)y * a.W + x;
+    if (inb) {
 
     const float4 mv = cur.mot(x, y);
-    const float4 g = make_guide(mv, cur.nrm(x, y), cur.uvw(x, y));
-    cur_guide[i] = g;
+    const GuideTexel g = make_guide(mv, cur.nrm(x, y), cur.uvw(x, y));
+    cur_guide.n[i] = g.n; cur_guide.dz[i] = g.dz; cur_guide.mid[i] = g.mid;
     const float4 c = clamp01(ColourPlane<F32>::decode(colour[i]));            // :370
 
     float3 pc = make_float3(0.f, 0.f, 0.f);
@@ -63,12 +77,18 @@ temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, const float4 *__res
     const int qx = x + __float2int_rz(mv.x), qy = y + __float2int_rz(mv.y);    // :232
     if (!a.force_fail && qx >= 0 && qx < a.W && qy >= 0 && qy < a.H) {         // :235
         const size_t qi = (size_t)qy * a.W + qx;
-        float4 pg;
-        if (PREV_GUIDE) pg = __ldg(prev_guide + qi);
-        else pg = make_guide(prev.mot(qx, qy), prev.nrm(qx, qy), prev.uvw(qx, qy));
-        ok = !(fabsf(pg.x - g.x) > a.depth_threshold);                         // :242
-        ok = ok && (a.vacuous_mesh_id || guide_mesh_id(g) == guide_mesh_id(pg));  // :245-247
-        ok = ok && !(dot3(guide_normal(g), guide_normal(pg)) < a.normal_threshold);  // :250-252
+        float4 pn;
+        unsigned short pmid;
+        if (PREV_GUIDE) {
+            pn = __ldg(prev_guide.n + qi);
+            pmid = __ldg(prev_guide.mid + qi);
+        } else {
+            const GuideTexel pg = make_guide(prev.mot(qx, qy), prev.nrm(qx, qy), prev.uvw(qx, qy));
+            pn = pg.n; pmid = pg.mid;
+        }
+        ok = !(fabsf(pn.x - g.n.x) > a.depth_threshold);                       // :242
+        ok = ok && (a.vacuous_mesh_id || guide_mesh_id(g.mid) == guide_mesh_id(pmid));  // :245-247
+        ok = ok && !(dot3(guide_normal(g.n), guide_normal(pn)) < a.normal_threshold);  // :250-252
         if (ok) {
             const float4 p4 = clamp01(ColourPlane<F32>::decode(__ldg(prev_colour + qi)));  // :254
             pc = make_float3(p4.x, p4.y, p4.z);
@@ -96,8 +116,25 @@ temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, const float4 *__res
     o.z = mix_rn(pc.z, c.z, alpha);
     o.w = var;
     hist_out[i] = (uint8_t)h;                                                  // :400
-    colour[i] = ColourPlane<F32>::encode(clamp01(o));                          // :401
+    const typename ColourPlane<F32>::texel enc = ColourPlane<F32>::encode(clamp01(o));
+    colour[i] = enc;                                                           // :401
     cur_mom[i] = MomentsPlane<F32>::encode(m);                                 // :402
+    if (fused.var_out) {
+        const bool zero_n = fused.zero_normal_shortcut && g.n.y == 0.0f && g.n.z == 0.0f && g.n.w == 0.0f;
+        queue = (h < 4) && !zero_n;
+        fused.var_out[i] = (h < 4 && zero_n) ? ColourPlane<F32>::encode(make_float4(0.f, 0.f, 0.f, 0.f)) : enc;
+    }
+    }
+    if (fused.var_out) {   // warp-aggregated append of the short-history pixels
+        const unsigned int m = __ballot_sync(0xffffffffu, queue);
+        if (m) {
+            const int lane = threadIdx.x & 31;
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(fused.counter, (unsigned int)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (queue) fused.worklist[base + __popc(m & ((1u << lane) - 1u))] = (unsigned int)i;
+        }
+    }
 }
 
 struct SpatialArgs {
@@ -107,36 +144,24 @@ struct SpatialArgs {
     int step, level;
 };
 
-// ---- variance estimation: reference filter::FilterMoments (src/Filter.cuh:430-525).  Also publishes the
-// history plane (hist_publish, may be null): the caller-visible buffer receives this frame's lengths here so
-// the temporal pass never reads and writes one plane in the same launch (D3).
+// ---- variance estimation: reference filter::FilterMoments (src/Filter.cuh:430-525) -------------------------
+// 7x7 cross-bilateral estimate for one short-history pixel (:446-516)
 template <bool F32, bool SERIES>
-__global__ void __launch_bounds__(256)
-variance_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename ColourPlane<F32>::texel *__restrict__ in,
-                const typename MomentsPlane<F32>::texel *__restrict__ mom, const uint8_t *__restrict__ hist,
-                uint8_t *__restrict__ hist_publish, typename ColourPlane<F32>::texel *__restrict__ out) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= a.W || y >= a.H) return;
+__device__ __forceinline__ typename ColourPlane<F32>::texel
+variance_7x7(const SpatialArgs &a, const Guide &guide, const typename ColourPlane<F32>::texel *__restrict__ in,
+             const typename MomentsPlane<F32>::texel *__restrict__ mom, int x, int y, float h) {
     const size_t i = (size_t)y * a.W + x;
-    const uint8_t hb = hist[i];
-    if (hist_publish) hist_publish[i] = hb;
-    if (hb >= 4) {                                                             // :444,:518-523
-        out[i] = in[i];
-        return;
-    }
-    const float h = (float)hb;
     const float4 cc = ColourPlane<F32>::decode(__ldg(in + i));                 // :450 (no clamp)
     const float lc = luminance(cc.x, cc.y, cc.z);
-    const float4 gc = __ldg(guide + i);
+    const float4 gc = __ldg(guide.n + i);
     const float3 nc = guide_normal(gc);
     if (nc.x == 0.0f && nc.y == 0.0f && nc.z == 0.0f && a.nt.phiN > 0.0f) {
         // zero centre normal (background, D7): every weight is exp(..) * pow(0, phiN) = 0, so the sums are 0 and
         // the output is exactly (0, 0, 0, 0) — same result as running the 49 taps.
-        out[i] = ColourPlane<F32>::encode(make_float4(0.f, 0.f, 0.f, 0.f));
-        return;
+        return ColourPlane<F32>::encode(make_float4(0.f, 0.f, 0.f, 0.f));
     }
     const float kL = kLog2e / a.phi_colour;                                    // :460
-    const float phiZ0 = fmaxf(gc.y, 1e-8f) * 3.0f * a.phi_depth;              // :461
+    const float phiZ0 = fmaxf(__ldg(guide.dz + i), 1e-8f) * 3.0f * a.phi_depth;  // :461
     float sw = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sm1 = 0.f, sm2 = 0.f;
     for (int yy = -3; yy <= 3; yy++) {
         const int py = y + yy;
@@ -147,7 +172,7 @@ variance_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename 
             const size_t qi = (size_t)py * a.W + px;
             const float4 cq = ColourPlane<F32>::decode(__ldg(in + qi));
             const float2 mq = MomentsPlane<F32>::decode(__ldg(mom + qi));
-            const float4 gq = __ldg(guide + qi);
+            const float4 gq = __ldg(guide.n + qi);
             const float lq = luminance(cq.x, cq.y, cq.z);
             const float phiZ = phiZ0 * sqrtf((float)(xx * xx + yy * yy));      // :488
             const float kZ = (phiZ == 0.0f) ? 0.0f : kLog2e / phiZ;            // :420
@@ -163,19 +188,53 @@ variance_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename 
     const float m1 = sm1 * inv, m2 = sm2 * inv;
     float var = m2 - m1 * m1;                                                  // :511
     var = var * (4.0f / h);                                                    // :514  (h in {0,1,2,3}; h == 0 only if the caller supplies it)
-    out[i] = ColourPlane<F32>::encode(make_float4(sr * inv, sg * inv, sb * inv, var));  // :516
+    return ColourPlane<F32>::encode(make_float4(sr * inv, sg * inv, sb * inv, var));  // :516
+}
+
+// Dense form (stand-alone svgf_variance).  Also publishes the history plane (hist_publish, may be null).
+template <bool F32, bool SERIES>
+__global__ void __launch_bounds__(256)
+variance_kernel(SpatialArgs a, Guide guide, const typename ColourPlane<F32>::texel *__restrict__ in,
+                const typename MomentsPlane<F32>::texel *__restrict__ mom, const uint8_t *__restrict__ hist,
+                uint8_t *__restrict__ hist_publish, typename ColourPlane<F32>::texel *__restrict__ out) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= a.W || y >= a.H) return;
+    const size_t i = (size_t)y * a.W + x;
+    const uint8_t hb = hist[i];
+    if (hist_publish) hist_publish[i] = hb;
+    if (hb >= 4) {                                                             // :444,:518-523
+        out[i] = in[i];
+        return;
+    }
+    out[i] = variance_7x7<F32, SERIES>(a, guide, in, mom, x, y, (float)hb);
+}
+
+// Sparse form (svgf_frame): only the pixels the temporal pass queued (history < 4, non-zero normal); every other
+// pixel of `out` was already written by the temporal pass.  Grid-stride over the worklist.
+template <bool F32, bool SERIES>
+__global__ void __launch_bounds__(256)
+variance_sparse_kernel(SpatialArgs a, Guide guide, const typename ColourPlane<F32>::texel *__restrict__ in,
+                       const typename MomentsPlane<F32>::texel *__restrict__ mom, const uint8_t *__restrict__ hist,
+                       const unsigned int *__restrict__ worklist, const unsigned int *__restrict__ counter,
+                       typename ColourPlane<F32>::texel *__restrict__ out) {
+    const unsigned int n = *counter;
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const unsigned int i = worklist[k];
+        const int y = (int)(i / (unsigned int)a.W), x = (int)(i - (unsigned int)y * (unsigned int)a.W);
+        out[i] = variance_7x7<F32, SERIES>(a, guide, in, mom, x, y, (float)hist[i]);
+    }
 }
 
 // ---- one a-trous level: reference filter::FilterKernel (src/Filter.cuh:527-624) ---------------------------
 template <bool F32, bool SERIES>
 __global__ void __launch_bounds__(256)
-atrous_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename ColourPlane<F32>::texel *__restrict__ in,
+atrous_kernel(SpatialArgs a, Guide guide, const typename ColourPlane<F32>::texel *__restrict__ in,
               typename ColourPlane<F32>::texel *__restrict__ out, typename ColourPlane<F32>::texel *__restrict__ hist_colour) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= a.W || y >= a.H) return;
     const size_t i = (size_t)y * a.W + x;
     const float4 c = clamp01(ColourPlane<F32>::decode(__ldg(in + i)));         // :543
-    const float4 gc = __ldg(guide + i);
+    const float4 gc = __ldg(guide.n + i);
     if (gc.x == kBackgroundZ) {                                                // :554-558
         out[i] = ColourPlane<F32>::encode(c);
         return;
@@ -184,7 +243,7 @@ atrous_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename Co
     const float3 nc = guide_normal(gc);
     const float phiL = a.phi_colour * sqrtf(fmaxf(0.0f, 1e-10f + c.w));        // :562
     const float kL = kLog2e / phiL;
-    const float phiZ = fmaxf(gc.y, 1e-6f) * (float)a.step * a.phi_depth;       // :563
+    const float phiZ = fmaxf(__ldg(guide.dz + i), 1e-6f) * (float)a.step * a.phi_depth;  // :563
     const float kZ1 = (phiZ == 0.0f) ? 0.0f : kLog2e / phiZ;
     const float KW[3] = {1.0f, (float)(2.0 / 3.0), (float)(1.0 / 6.0)};        // :540
     float sw = 1.0f, sr = c.x, sg = c.y, sb = c.z, sv = c.w;                   // :567-568
@@ -198,7 +257,7 @@ atrous_kernel(SpatialArgs a, const float4 *__restrict__ guide, const typename Co
             if (px < 0 || px >= a.W || (xx == 0 && yy == 0)) continue;         // :579,:584
             const size_t qi = (size_t)py * a.W + px;
             const float4 cq = clamp01(ColourPlane<F32>::decode(__ldg(in + qi)));  // :586
-            const float4 gq = __ldg(guide + qi);
+            const float4 gq = __ldg(guide.n + qi);
             const float lq = luminance(cq.x, cq.y, cq.z);
             const float kZ = kZ1 / sqrtf((float)(xx * xx + yy * yy));          // phiZ * length(xx,yy), :595
             const float e = edge_exponent<SERIES>(fmaf(fabsf(gc.x - gq.x), kZ, fabsf(lc - lq) * kL), dot3(nc, guide_normal(gq)), a.nt);

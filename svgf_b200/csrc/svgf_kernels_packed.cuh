@@ -1,0 +1,281 @@
+// svgf_kernels_packed.cuh — the a-trous level with packed FP32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2).
+//
+// The level is bound by instruction issue before it is bound by the FP32 pipe (ncu on the scalar tiled kernel:
+// issue slots 65 % busy with 1.5 eligible warps per scheduler, FMA pipe 45 %; tools/microbench.cu: FFMA2 retires
+// two FMAs per issue slot at the same FMA throughput).  So each thread filters TWO horizontally adjacent outputs
+// (x, x+1) at once and every FP32 instruction of the tap evaluation is the packed .f32x2 form: ~11 issue slots
+// per tap instead of ~28.
+//
+// What makes the packing free of shuffles and moves:
+//  * shared memory holds PIXEL PAIRS interleaved per channel — {r0,r1,g0,g1} {b0,b1,v0,v1} {z0,z1,nx0,nx1}
+//    {ny0,ny1,nz0,nz1} {l0,l1} — so one LDS.128 delivers two ready-made 64-bit register pairs; the taps of outputs
+//    (x, x+1) at offset dx*STEP are the stored pair at column x + dx*STEP whenever dx*STEP is even;
+//  * the per-output quantities (centre luminance, depth, normal, the two edge-stopping scales, the five sums) are
+//    natural pairs; per-tap constants (kernel weight, 1/length) are immediates broadcast by the instruction;
+//  * level 0 (STEP = 1) has odd offsets: dx = +-1 taps are evaluated with the scalar form on the halves of the three
+//    aligned pairs that are loaded anyway (dx = -2, 0, +2 stay packed).
+// Everything else follows svgf_kernels_tiled.cuh: one lattice row phase per tile, contiguous 128-pixel x range,
+// R outputs per thread and column for register-level tap reuse, per-pixel work (decode, clamp, luminance) done once
+// at staging, null texels (z = +inf) outside the image.  Arithmetic and rounding are identical to the scalar
+// kernels (fma.rn.f32x2 is two independent fma.rn.f32).
+#pragma once
+#include "svgf_device.cuh"
+#include "svgf_kernels_tiled.cuh"
+
+namespace svgf {
+
+constexpr int kPkRows = 3;        // outputs per thread and column (R)
+constexpr int kPkRowGroups = 4;   // row groups per CTA
+constexpr int kPkPairs = kTileW / 2;
+constexpr int kPkThreads = kPkPairs * kPkRowGroups;   // 256
+
+template <int STEP> struct PackedGeom {
+    static constexpr int tile_rows = kPkRows * kPkRowGroups;       // 12
+    static constexpr int cols = kTileW + 4 * STEP;
+    static constexpr int pairs = cols / 2;
+    static constexpr int rows = tile_rows + 4;
+    static constexpr int npairs = pairs * rows;
+    static constexpr size_t smem_bytes = (size_t)npairs * 72;
+};
+
+__device__ __forceinline__ float2 f2abs(float2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
+__device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 f2bc(float a) { return make_float2(a, a); }
+
+struct PkCentre { float2 lc, zc, nx, ny, nz, kL, kZ; };
+struct PkAcc { float2 S, r, g, b, v; };
+struct PkTap { float2 r, g, b, v, l, z, nx, ny, nz; };
+struct PkCoef { float k1, k2, k3, k4, k5; };
+
+// one tap for both outputs of the pair; ck = -log2(kernel weight), cinv = 1/length(xx,yy)
+template <int TERMS>
+__device__ __forceinline__ void pk_tap2(PkAcc &A, const PkCentre &C, const PkTap &q, float ck, float cinv, const PkCoef &k) {
+    float2 base = __ffma2_rn(f2abs(__fadd2_rn(q.l, f2neg(C.lc))), C.kL, f2bc(ck));
+    const float2 tz = __fmul2_rn(f2abs(__fadd2_rn(q.z, f2neg(C.zc))), C.kZ);
+    base = __ffma2_rn(tz, f2bc(cinv), base);
+    float2 d = __fmul2_rn(C.nx, q.nx);                      // (x*x' + y*y') + z*z', reference dot order
+    d = __ffma2_rn(C.ny, q.ny, d);
+    d = __ffma2_rn(C.nz, q.nz, d);
+    float2 u = __fadd2_rn(f2bc(1.0f), f2neg(d));
+    u = make_float2(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));    // d > 1 saturates to 1 (u = 0); d < 0 gives u > 1: weight ~ 2^-96
+    float2 p;
+    if (TERMS == 5) { p = __ffma2_rn(u, f2bc(k.k5), f2bc(k.k4)); p = __ffma2_rn(u, p, f2bc(k.k3)); }
+    else p = __ffma2_rn(u, f2bc(k.k4), f2bc(k.k3));
+    p = __ffma2_rn(u, p, f2bc(k.k2));
+    p = __ffma2_rn(u, p, f2bc(k.k1));
+    const float2 e = __ffma2_rn(f2neg(u), p, f2neg(base));
+    const float2 w = make_float2(fast_exp2(e.x), fast_exp2(e.y));
+    A.S = __fadd2_rn(A.S, w);
+    A.r = __ffma2_rn(w, q.r, A.r);
+    A.g = __ffma2_rn(w, q.g, A.g);
+    A.b = __ffma2_rn(w, q.b, A.b);
+    A.v = __ffma2_rn(__fmul2_rn(w, w), q.v, A.v);
+}
+
+// scalar form for one output and one tap (level 0, odd dx)
+template <int TERMS>
+__device__ __forceinline__ void pk_tap1(float &S, float &Ar, float &Ag, float &Ab, float &Av, float lc, float zc, float nx, float ny,
+                                        float nz, float kL, float kZ, float ql, float qz, float qnx, float qny, float qnz, float qr,
+                                        float qg, float qb, float qv, float ck, float cinv, const PkCoef &k) {
+    float base = fmaf(fabsf(ql - lc), kL, ck);
+    base = fmaf(fabsf(qz - zc) * kZ, cinv, base);
+    const float d = fmaf(nz, qnz, fmaf(ny, qny, nx * qnx));
+    const float u = fmaxf(1.0f - d, 0.0f);
+    float p;
+    if (TERMS == 5) { p = fmaf(u, k.k5, k.k4); p = fmaf(u, p, k.k3); }
+    else p = fmaf(u, k.k4, k.k3);
+    p = fmaf(u, p, k.k2);
+    p = fmaf(u, p, k.k1);
+    const float w = fast_exp2(fmaf(-u, p, -base));
+    S += w;
+    Ar = fmaf(w, qr, Ar); Ag = fmaf(w, qg, Ag); Ab = fmaf(w, qb, Ab);
+    Av = fmaf(w * w, qv, Av);
+}
+
+__device__ __forceinline__ constexpr float tap_inv_len(int ax, int ay) {
+    const int l2 = ax * ax + ay * ay;   // 1 2 4 5 8
+    return l2 == 1 ? 1.0f : l2 == 2 ? 0.70710678f : l2 == 4 ? 0.5f : l2 == 5 ? 0.44721360f : 0.35355339f;
+}
+
+template <bool F32, int STEP, int TERMS>
+__global__ void __launch_bounds__(kPkThreads, 2)
+atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, const float *__restrict__ guide_dz,
+                     const typename ColourPlane<F32>::texel *__restrict__ in, typename ColourPlane<F32>::texel *__restrict__ out,
+                     typename ColourPlane<F32>::texel *__restrict__ hist_colour) {
+    using G = PackedGeom<STEP>;
+    using CT = typename ColourPlane<F32>::texel;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *sC0 = reinterpret_cast<float4 *>(smem_raw);        // r0 r1 g0 g1
+    float4 *sC1 = sC0 + G::npairs;                             // b0 b1 v0 v1
+    float4 *sG0 = sC1 + G::npairs;                             // z0 z1 nx0 nx1
+    float4 *sG1 = sG0 + G::npairs;                             // ny0 ny1 nz0 nz1
+    float2 *sL = reinterpret_cast<float2 *>(sG1 + G::npairs);  // l0 l1
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * kTileW;
+    const int yblock = blockIdx.y / STEP, phase = blockIdx.y % STEP;
+    const int y0 = yblock * (G::tile_rows * STEP) + phase;
+
+    // ---- stage the tile, one pixel pair per thread and iteration; all global loads first ----
+    constexpr int kIters = (G::npairs + kPkThreads - 1) / kPkThreads;
+    CT rc0[kIters], rc1[kIters];
+    float4 rg0[kIters], rg1[kIters];
+#pragma unroll
+    for (int i = 0; i < kIters; i++) {
+        const int idx = tid + i * kPkThreads;
+        const int r = idx / G::pairs, pc = idx - r * G::pairs;
+        const int gx = x0 - 2 * STEP + 2 * pc, gy = y0 + (r - 2) * STEP;
+        rg0[i] = rg1[i] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);   // null texel: z = +inf, zero normal
+        rc0[i] = rc1[i] = CT();
+        if (idx < G::npairs && gx >= 0 && gx < a.W && gy >= 0 && gy < a.H) {       // W is even: a pair is inside or outside
+            const size_t gi = (size_t)gy * a.W + gx;
+            if (F32) {
+                rc0[i] = __ldg(in + gi);
+                rc1[i] = __ldg(in + gi + 1);
+            } else {
+                const uint4 t = __ldg(reinterpret_cast<const uint4 *>(in + gi));
+                *reinterpret_cast<uint2 *>(&rc0[i]) = make_uint2(t.x, t.y);
+                *reinterpret_cast<uint2 *>(&rc1[i]) = make_uint2(t.z, t.w);
+            }
+            rg0[i] = __ldg(guide_n + gi);
+            rg1[i] = __ldg(guide_n + gi + 1);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kIters; i++) {
+        const int idx = tid + i * kPkThreads;
+        if (idx < G::npairs) {
+            const float4 c0 = ColourPlane<F32>::decode(rc0[i]), c1 = ColourPlane<F32>::decode(rc1[i]);
+            const float r0 = __saturatef(c0.x), g0 = __saturatef(c0.y), b0 = __saturatef(c0.z), v0 = __saturatef(c0.w);   // :543,:586
+            const float r1 = __saturatef(c1.x), g1 = __saturatef(c1.y), b1 = __saturatef(c1.z), v1 = __saturatef(c1.w);
+            sC0[idx] = make_float4(r0, r1, g0, g1);
+            sC1[idx] = make_float4(b0, b1, v0, v1);
+            sG0[idx] = make_float4(rg0[i].x, rg1[i].x, rg0[i].y, rg1[i].y);
+            sG1[idx] = make_float4(rg0[i].z, rg1[i].z, rg0[i].w, rg1[i].w);
+            sL[idx] = make_float2(luminance(r0, g0, b0), luminance(r1, g1, b1));
+        }
+    }
+    __syncthreads();
+
+    const int pcx = tid & (kPkPairs - 1), tg = tid / kPkPairs;
+    const int gx = x0 + 2 * pcx;
+    const int pcol = pcx + STEP;                      // pair column in shared memory (halo of 2*STEP pixels = STEP pairs)
+    const int row0 = tg * kPkRows + 2;
+    PkCoef k;
+    k.k1 = a.k1; k.k2 = a.k2; k.k3 = a.k3; k.k4 = a.k4; k.k5 = a.k5;
+
+    PkCentre C[kPkRows];
+    PkAcc A[kPkRows];
+    bool live0[kPkRows], live1[kPkRows];
+    bool any_live = false;
+#pragma unroll
+    for (int j = 0; j < kPkRows; j++) {
+        const int si = (row0 + j) * G::pairs + pcol;
+        const float4 c0 = sC0[si], c1 = sC1[si], g0 = sG0[si], g1 = sG1[si];
+        const int gy = y0 + (tg * kPkRows + j) * STEP;
+        A[j].S = f2bc(1.0f);                                                       // :567-568
+        A[j].r = make_float2(c0.x, c0.y); A[j].g = make_float2(c0.z, c0.w);
+        A[j].b = make_float2(c1.x, c1.y); A[j].v = make_float2(c1.z, c1.w);
+        C[j].lc = sL[si];
+        C[j].zc = make_float2(g0.x, g0.y); C[j].nx = make_float2(g0.z, g0.w);
+        C[j].ny = make_float2(g1.x, g1.y); C[j].nz = make_float2(g1.z, g1.w);
+        const bool inside = (gx < a.W) && (gy < a.H);
+        live0[j] = inside && (g0.x != kBackgroundZ);                               // :554: background passes through
+        live1[j] = inside && (g0.y != kBackgroundZ);
+        any_live |= live0[j] | live1[j];
+        C[j].kL = make_float2(a.kL_scale * rsqrtf(1e-10f + c1.z), a.kL_scale * rsqrtf(1e-10f + c1.w));   // :562
+        float2 dz = make_float2(0.f, 0.f);
+        if (inside) dz = __ldg(reinterpret_cast<const float2 *>(guide_dz + (size_t)gy * a.W + gx));
+        C[j].kZ = make_float2(__fdividef(a.kZ_scale, fmaxf(dz.x, 1e-6f)), __fdividef(a.kZ_scale, fmaxf(dz.y, 1e-6f)));   // :563
+    }
+
+    if (__any_sync(0xffffffffu, any_live)) {
+        if (STEP > 1) {
+#pragma unroll
+            for (int dx = -2; dx <= 2; dx++) {
+#pragma unroll
+                for (int t = -2; t < kPkRows + 2; t++) {
+                    const int si = (row0 + t) * G::pairs + pcol + dx * (STEP / 2);
+                    const float4 c0 = sC0[si], c1 = sC1[si], g0 = sG0[si], g1 = sG1[si];
+                    PkTap q;
+                    q.r = make_float2(c0.x, c0.y); q.g = make_float2(c0.z, c0.w); q.b = make_float2(c1.x, c1.y); q.v = make_float2(c1.z, c1.w);
+                    q.z = make_float2(g0.x, g0.y); q.nx = make_float2(g0.z, g0.w); q.ny = make_float2(g1.x, g1.y); q.nz = make_float2(g1.z, g1.w);
+                    q.l = sL[si];
+#pragma unroll
+                    for (int j = 0; j < kPkRows; j++) {
+                        const int dy = t - j;
+                        if (dy < -2 || dy > 2 || (dx == 0 && dy == 0)) continue;
+                        const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
+                        pk_tap2<TERMS>(A[j], C[j], q, tap_neg_log2_kernel(ax, ay), tap_inv_len(ax, ay), k);
+                    }
+                }
+            }
+        } else {
+            // level 0: the six columns x-2 .. x+3 are the three aligned pairs m = -1, 0, +1.  Pair m serves dx = 2m packed
+            // (outputs x and x+1 tap columns x+2m and x+1+2m) and the odd offsets on its halves: output 0 (column x)
+            // taps x-1 = pair(-1).hi and x+1 = pair(0).hi; output 1 (column x+1) taps x = pair(0).lo and x+2 = pair(+1).lo.
+            // One pair is live at a time.
+#pragma unroll
+            for (int t = -2; t < kPkRows + 2; t++) {
+#pragma unroll
+                for (int m = -1; m <= 1; m++) {
+                    const int si = (row0 + t) * G::pairs + pcol + m;
+                    const float4 c0 = sC0[si], c1 = sC1[si], g0 = sG0[si], g1 = sG1[si];
+                    PkTap q;
+                    q.r = make_float2(c0.x, c0.y); q.g = make_float2(c0.z, c0.w); q.b = make_float2(c1.x, c1.y); q.v = make_float2(c1.z, c1.w);
+                    q.z = make_float2(g0.x, g0.y); q.nx = make_float2(g0.z, g0.w); q.ny = make_float2(g1.x, g1.y); q.nz = make_float2(g1.z, g1.w);
+                    q.l = sL[si];
+#pragma unroll
+                    for (int j = 0; j < kPkRows; j++) {
+                        const int dy = t - j;
+                        if (dy < -2 || dy > 2) continue;
+                        const int ay = dy < 0 ? -dy : dy;
+                        if (!(m == 0 && dy == 0))
+                            pk_tap2<TERMS>(A[j], C[j], q, tap_neg_log2_kernel(m == 0 ? 0 : 2, ay), tap_inv_len(m == 0 ? 0 : 2, ay), k);
+                        const float ck = tap_neg_log2_kernel(1, ay), ci = tap_inv_len(1, ay);
+                        if (m <= 0)   // output 0 <- this pair's hi half (x-1 for m = -1, x+1 for m = 0)
+                            pk_tap1<TERMS>(A[j].S.x, A[j].r.x, A[j].g.x, A[j].b.x, A[j].v.x, C[j].lc.x, C[j].zc.x, C[j].nx.x, C[j].ny.x,
+                                           C[j].nz.x, C[j].kL.x, C[j].kZ.x, q.l.y, q.z.y, q.nx.y, q.ny.y, q.nz.y, q.r.y, q.g.y, q.b.y, q.v.y,
+                                           ck, ci, k);
+                        if (m >= 0)   // output 1 <- this pair's lo half (x for m = 0, x+2 for m = +1)
+                            pk_tap1<TERMS>(A[j].S.y, A[j].r.y, A[j].g.y, A[j].b.y, A[j].v.y, C[j].lc.y, C[j].zc.y, C[j].nx.y, C[j].ny.y,
+                                           C[j].nz.y, C[j].kL.y, C[j].kZ.y, q.l.x, q.z.x, q.nx.x, q.ny.x, q.nz.x, q.r.x, q.g.x, q.b.x, q.v.x,
+                                           ck, ci, k);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- normalise and store both pixels of the pair (:615-622) ----
+#pragma unroll
+    for (int j = 0; j < kPkRows; j++) {
+        const int gy = y0 + (tg * kPkRows + j) * STEP;
+        if (gx >= a.W || gy >= a.H) continue;
+        const size_t gi = (size_t)gy * a.W + gx;
+        const int si = (row0 + j) * G::pairs + pcol;
+        const float4 c0 = sC0[si], c1 = sC1[si];
+        const float i0 = __frcp_rn(A[j].S.x), i1 = __frcp_rn(A[j].S.y);
+        float4 o0 = make_float4(A[j].r.x * i0, A[j].g.x * i0, A[j].b.x * i0, A[j].v.x * (i0 * i0));
+        float4 o1 = make_float4(A[j].r.y * i1, A[j].g.y * i1, A[j].b.y * i1, A[j].v.y * (i1 * i1));
+        if (!live0[j]) o0 = make_float4(c0.x, c0.z, c1.x, c1.z);                     // :556 (clamped centre)
+        if (!live1[j]) o1 = make_float4(c0.y, c0.w, c1.y, c1.w);
+        const CT e0 = ColourPlane<F32>::encode(o0), e1 = ColourPlane<F32>::encode(o1);
+        const bool h0 = (a.level == 0) && hist_colour && live0[j], h1 = (a.level == 0) && hist_colour && live1[j];
+        if (F32) {
+            out[gi] = e0; out[gi + 1] = e1;
+            if (h0) hist_colour[gi] = e0;
+            if (h1) hist_colour[gi + 1] = e1;
+        } else {
+            const uint2 u0 = *reinterpret_cast<const uint2 *>(&e0), u1 = *reinterpret_cast<const uint2 *>(&e1);
+            *reinterpret_cast<uint4 *>(out + gi) = make_uint4(u0.x, u0.y, u1.x, u1.y);
+            if (h0 && h1) *reinterpret_cast<uint4 *>(hist_colour + gi) = make_uint4(u0.x, u0.y, u1.x, u1.y);
+            else {
+                if (h0) hist_colour[gi] = e0;
+                if (h1) hist_colour[gi + 1] = e1;
+            }
+        }
+    }
+}
+
+}  // namespace svgf

@@ -140,11 +140,12 @@ def test_pan_sequence_matches_reference_where_the_history_race_is_benign():
     o = OracleFilter(W, H, storage="f16")
     o.params.mesh_id_mode = _lib.SVGF_MESH_ID_REFERENCE_VACUOUS
     o.params.atrous_iterations = 2
+    o.params.history_cap = 3          # lengths saturate after three frames: reads of a saturated length are benign
     rp = RefParams.from_svgf(o.params)
     r = RefKernels(W, H)
     o.Reset()
     compared = 0
-    for t in range(6):
+    for t in range(8):
         planes = synth.frame_host(W, H, t)
         o.set_inputs(planes)
         r.load_state(o)
@@ -168,7 +169,7 @@ def test_pan_sequence_matches_reference_where_the_history_race_is_benign():
         assert e["violations"] == 0, f"frame {t}: {e}"
         compared += int(benign.sum())
         o.FilterMoments(); o.WaveletFilter(); o.EndFrame()
-    assert compared > 0.5 * 6 * W * H
+    assert compared > 0.4 * 8 * W * H
     r.close()
 
 
