@@ -11,6 +11,7 @@
 #include "svgf_kernels_basic.cuh"
 #include "svgf_kernels_tiled.cuh"
 #include "svgf_kernels_packed.cuh"
+#include "svgf_kernels_stream.cuh"
 #include <cstdlib>
 
 using namespace svgf;
@@ -264,6 +265,46 @@ svgf_status dispatch_atrous_packed(svgf_ctx *c, const AtrousTiledArgs &a, int gu
     return SVGF_UNSUPPORTED;
 }
 
+template <bool F32, int STEP, int TERMS>
+svgf_status launch_atrous_stream(svgf_ctx *c, const AtrousTiledArgs &t, int guide_slot, const void *in, void *out, void *hist_colour,
+                                 cudaStream_t s) {
+    using CT = typename ColourPlane<F32>::texel;
+    using G = StreamGeom<STEP>;
+    auto kern = atrous_stream_kernel<F32, STEP, TERMS>;
+    static bool configured[16] = {};
+    const size_t smem = G::smem_bytes;
+    if (!configured[c->device & 15]) {
+        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[c->device & 15] = true;
+    }
+    AtrousStreamArgs a;
+    a.t = t;
+    a.n_strips = (c->W + kStripW - 1) / kStripW;
+    a.rows_a = c->H / STEP;
+    a.rows_b = c->H % STEP;
+    // the (strip, phase, row) stream is cut into equal contiguous ranges, one per CTA; two CTAs per SM
+    const long long T = (long long)a.n_strips * c->H;
+    long long grid = 2LL * c->num_sms;
+    if (grid > T / 8) grid = T / 8 > 0 ? T / 8 : 1;
+    kern<<<(unsigned int)grid, kStreamThreads, smem, s>>>(a, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in,
+                                                                    (CT *)out, (CT *)hist_colour);
+    c->launches++;
+    SVGF_CUDA(c, cudaGetLastError());
+    return SVGF_OK;
+}
+template <bool F32, int TERMS>
+svgf_status dispatch_atrous_stream(svgf_ctx *c, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out,
+                                   void *hist_colour, cudaStream_t s) {
+    switch (a.level) {
+        case 0: return launch_atrous_stream<F32, 1, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 1: return launch_atrous_stream<F32, 2, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 2: return launch_atrous_stream<F32, 4, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 3: return launch_atrous_stream<F32, 8, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+        case 4: return launch_atrous_stream<F32, 16, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
+    }
+    return SVGF_UNSUPPORTED;
+}
+
 // Row groups per CTA: 2 (256 threads, two CTAs per SM) while the tile fits twice; 4 (512 threads, one CTA per SM,
 // less vertical halo) for the wide-halo levels — chosen so every instantiation fits the 227 KB of shared memory.
 template <bool F32, int TERMS>
@@ -298,6 +339,14 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
         // SVGF_ATROUS_VARIANT=bulk selects the persistent bulk-copy (UBLKCP) scalar kernel for A/B measurements
         static const char *variant = getenv("SVGF_ATROUS_VARIANT");
         const bool want_bulk = variant && !strcmp(variant, "bulk");
+        const bool want_stream = variant && !strcmp(variant, "stream");
+        const bool pair_ok = c->W % 2 == 0 && ((uintptr_t)out % 16) == 0 && (!hist_colour || ((uintptr_t)hist_colour % 16) == 0);
+        // default: packed FP32x2 tiled kernel.  SVGF_ATROUS_VARIANT=stream selects the warp-specialised streaming kernel
+        // (register sliding window; a third of the shared-memory traffic but two consumer warps per sub-partition —
+        // measured slower), =bulk the persistent bulk-copy scalar kernel
+        if (want_stream && pair_ok)
+            return (p->phi_normal >= 100.0f) ? dispatch_atrous_stream<F32, 4>(c, t, guide_slot, in, out, hist_colour, s)
+                                             : dispatch_atrous_stream<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);
         if (!want_bulk && c->W % 2 == 0 && ((uintptr_t)out % 16) == 0 && (!hist_colour || ((uintptr_t)hist_colour % 16) == 0))
             return (p->phi_normal >= 100.0f) ? dispatch_atrous_packed<F32, 4>(c, t, guide_slot, in, out, hist_colour, s)
                                              : dispatch_atrous_packed<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);

@@ -72,6 +72,33 @@ __device__ __forceinline__ void pk_tap2(PkAcc &A, const PkCentre &C, const PkTap
     A.v = __ffma2_rn(__fmul2_rn(w, w), q.v, A.v);
 }
 
+// same tap with the centre's luminance and depth stored NEGATED (nlc = -lc, nzc = -zc): inside a rolled loop the
+// compiler otherwise hoists the two negations into extra live registers per output
+struct PkCentreN { float2 nlc, nzc, nx, ny, nz, kL, kZ; };
+template <int TERMS>
+__device__ __forceinline__ void pk_tap2n(PkAcc &A, const PkCentreN &C, const PkTap &q, float ck, float cinv, const PkCoef &k) {
+    float2 base = __ffma2_rn(f2abs(__fadd2_rn(q.l, C.nlc)), C.kL, f2bc(ck));
+    const float2 tz = __fmul2_rn(f2abs(__fadd2_rn(q.z, C.nzc)), C.kZ);
+    base = __ffma2_rn(tz, f2bc(cinv), base);
+    float2 d = __fmul2_rn(C.nx, q.nx);                      // (x*x' + y*y') + z*z', reference dot order
+    d = __ffma2_rn(C.ny, q.ny, d);
+    d = __ffma2_rn(C.nz, q.nz, d);
+    float2 u = __fadd2_rn(f2bc(1.0f), f2neg(d));
+    u = make_float2(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));
+    float2 p;
+    if (TERMS == 5) { p = __ffma2_rn(u, f2bc(k.k5), f2bc(k.k4)); p = __ffma2_rn(u, p, f2bc(k.k3)); }
+    else p = __ffma2_rn(u, f2bc(k.k4), f2bc(k.k3));
+    p = __ffma2_rn(u, p, f2bc(k.k2));
+    p = __ffma2_rn(u, p, f2bc(k.k1));
+    const float2 e = __ffma2_rn(f2neg(u), p, f2neg(base));
+    const float2 w = make_float2(fast_exp2(e.x), fast_exp2(e.y));
+    A.S = __fadd2_rn(A.S, w);
+    A.r = __ffma2_rn(w, q.r, A.r);
+    A.g = __ffma2_rn(w, q.g, A.g);
+    A.b = __ffma2_rn(w, q.b, A.b);
+    A.v = __ffma2_rn(__fmul2_rn(w, w), q.v, A.v);
+}
+
 // scalar form for one output and one tap (level 0, odd dx)
 template <int TERMS>
 __device__ __forceinline__ void pk_tap1(float &S, float &Ar, float &Ag, float &Ab, float &Av, float lc, float zc, float nx, float ny,

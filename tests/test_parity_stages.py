@@ -203,3 +203,15 @@ def test_argument_validation_through_the_abi():
     assert _lib.lib().svgf_create(C.byref(ctx), 0, 0, 16, 0) == _lib.SVGF_INVALID_ARG
     assert _lib.lib().svgf_create(C.byref(ctx), 99, 16, 16, 0) == _lib.SVGF_CUDA_ERROR
     assert _lib.lib().svgf_create(C.byref(ctx), 0, 16, 16, 7) == _lib.SVGF_INVALID_ARG
+
+
+@pytest.mark.parametrize("variant", ["stream", "bulk"])
+def test_atrous_kernel_variants_meet_the_same_bar(variant):
+    # SVGF_ATROUS_VARIANT is read once per process: run the a-trous parity tests of this file in a child process
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, SVGF_ATROUS_VARIANT=variant)
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-m", "gpu", "-q", "-x", "-k", "atrous_single_level or atrous_cascade",
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
