@@ -279,6 +279,82 @@ def run_ours(args, rank, world, local):
     return line
 
 
+def run_bands(args, rank, world, local):
+    """--mode bands (BASELINE configs[3]): ONE frame stream, every frame split into `world` horizontal bands with
+    per-level halo rows exchanged between neighbouring ranks (NCCL send/recv over NVLink); strong scaling."""
+    import torch
+    from svgf_b200 import synth
+    from svgf_b200.bands import APRON, make_gpu_banded_filter
+    from svgf_b200.filter import GBuffer
+    W, H = WORKLOADS[args.workload]
+    dev = torch.device("cuda", local)
+    K, Wm = args.steps, args.warmup
+    R = K + Wm
+    bf = make_gpu_banded_filter(W, H, rank, world, dev, storage=args.storage, levels=args.levels)
+    f, band = bf.f, bf.band
+    Hl = band.local_height
+    cdt = torch.float16 if args.storage == "f16" else torch.float32
+    # every rank generates the full frames procedurally on its own GPU and keeps only its local rows (band + aprons)
+    full_g, full_c = GBuffer(W, H, dev), torch.empty(H, W, 4, dtype=cdt, device=dev)
+    ring_g = [GBuffer(W, Hl, dev) for _ in range(R)]
+    ring_c = [torch.empty(Hl, W, 4, dtype=cdt, device=dev) for _ in range(R)]
+    for t in range(R):
+        synth.frame_device(full_g, full_c, t, seed=0)
+        sl = slice(band.ly0, band.ly1)
+        ring_g[t].normal.copy_(full_g.normal[sl]); ring_g[t].uv.copy_(full_g.uv[sl]); ring_g[t].motion.copy_(full_g.motion[sl])
+        ring_c[t].copy_(full_c[sl])
+    del full_g, full_c
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream(dev)
+    f.Reset()
+
+    def step(t):
+        P = f.PingPongInx
+        f.Framebuffer[P], f.RenderBuffer[P] = ring_g[t], ring_c[t]      # inputs are consumed in place, no copies
+        bf.Filter()
+        bf.EndFrame()
+
+    for t in range(Wm):
+        step(t)
+    barrier(world)
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    launches0 = f.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(Wm, Wm + K):
+        step(t)
+    e1.record(stream)
+    barrier(world)
+    sampler.stop_flag = True
+    ms_max = max_over_ranks(e0.elapsed_time(e1), world)
+    launches = sum_over_ranks(f.launches - launches0, world)
+    sampler.join()
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peaks()
+    bpp = BYTES_PER_PX[args.storage]
+    frame_bytes = (bpp["temporal"] + bpp["variance"] + bpp["atrous_level"] * args.levels + (bpp["atrous_hist"] if args.levels else 0)) * W * H
+    halo_rows = sum(2 << i for i in range(args.levels)) + 3 * 0
+    halo_bytes = 2 * (world - 1) * (halo_rows * W * OUT_BYTES_PER_PX[args.storage] + APRON * W * (OUT_BYTES_PER_PX[args.storage] * 3 // 2 + 1))
+    value = W * H * K / (ms_max * 1e-3) / 1e9
+    return {
+        "metric": "svgf_frame_throughput", "value": round(value, 4), "unit": "Gpix/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": round(ms_max / K, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 compute, %s storage" % ("fp16" if args.storage == "f16" else "fp32"), "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[3]: {W}x{H} frames in {world} horizontal band(s), temporal + variance + {args.levels} "
+                               f"a-trous levels, per-level halo exchange (NCCL send/recv)", "width": W, "height": H,
+                   "atrous_levels": args.levels, "storage": args.storage, "band_rows": band.y1 - band.y0, "apron_rows": APRON,
+                   "halo_bytes_per_frame_all_ranks": int(halo_bytes),
+                   "l2": "every step reads a fresh frame"},
+        "gpu_launches": int(launches),
+        "frame_roofline": {"algorithmic_bytes": int(frame_bytes), "achieved": round(frame_bytes / (ms_max / K * 1e-3) / 1e9, 1),
+                           "frac_of_n_gpu_peak": round(frame_bytes / (ms_max / K * 1e-3) / 1e9 / (peak * world), 4), "unit": "GB/s",
+                           "peak_source": peak_src},
+        "clocks": sampler.result(),
+    }
+
+
 def cpu_baseline(args):
     """The scalar oracle on the host cores, on a bounded sample of the workload (rank 0, N = 1)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -401,6 +477,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=24)
     ap.add_argument("--cpu-budget-px", type=float, default=1.6e6, help="pixels per frame of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="streams", choices=["streams", "bands"],
+                    help="multi-GPU sharding: independent frame streams per GPU (weak scaling, default) or one frame in "
+                         "horizontal bands with per-level halo exchange (strong scaling; BASELINE configs[3], use --workload 8k)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -413,6 +492,8 @@ def main():
     rank, world, local = dist_setup(args.gpus)
     if args.impl == "reference":
         line = run_reference(args, rank, world, local)
+    elif args.mode == "bands":
+        line = run_bands(args, rank, world, local)
     else:
         line = run_ours(args, rank, world, local)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -1,0 +1,170 @@
+"""Band partition of one frame across ranks (svgf_b200/bands.py, BASELINE config 4).
+
+CPU: world_size-2 gloo run with the scalar oracle as the per-band backend — the stitched bands must be BIT-IDENTICAL
+to the oracle on the whole frame (every band pixel sees exactly the inputs it would see in the full image once the
+per-level halo rows and the previous-frame state aprons have been exchanged).  GPU (-m gpu): the same through the C
+ABI on one device, two bands exchanged in-process, against the unpartitioned CUDA path."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle_lib import OracleFilter, oracle
+from svgf_b200 import synth
+from svgf_b200.bands import APRON, BandedFilter, band_of, check_partition
+
+W, H, FRAMES, LEVELS = 64, 96, 3, 5
+
+
+def test_band_geometry():
+    for world in (1, 2, 3, 4, 8):
+        rows = []
+        for r in range(world):
+            b = band_of(4320, world, r)
+            assert b.ly0 == max(0, b.y0 - APRON) and b.ly1 == min(4320, b.y1 + APRON)
+            rows += list(range(b.y0, b.y1))
+        assert rows == list(range(4320))                      # bands tile the frame exactly once
+    check_partition(4320, 8, 5)
+    with pytest.raises(ValueError):
+        check_partition(96, 8, 5)                             # 12-row bands cannot feed a 32-row halo
+    with pytest.raises(ValueError):
+        check_partition(4320, 2, 6)                           # a sixth level needs a 64-row apron
+
+
+# ---- oracle backend for BandedFilter -------------------------------------------------------------------------------
+def _o_temporal_variance(o):
+    o.TemporalFilter()
+    o.FilterMoments()
+    return o.FilterBuffer[0]
+
+
+def _o_atrous_level(o, level, src, dst):
+    g = o.gbuf(o.PingPongInx)
+    rc = oracle().svgf_oracle_atrous_level(C.byref(o.params), o.Width, o.Height, o.storage, C.byref(g), src.ctypes.data,
+                                           dst.ctypes.data, o.RenderBuffer[o.PingPongInx].ctypes.data, level)
+    assert rc == 0
+
+
+def _as_tensor(a):
+    return torch.from_numpy(a.reshape(a.shape[0], -1).view(np.uint8))      # rows x bytes, shares memory
+
+
+ORACLE_OPS = {"temporal_variance": _o_temporal_variance, "atrous_level": _o_atrous_level, "as_tensor": _as_tensor}
+
+
+def _frames():
+    # vertical motion of ~2.5 px/frame so that reprojection crosses the band boundary
+    return [synth.frame_host(W, H, t, vert_px=2.5) for t in range(FRAMES)]
+
+
+def _full_oracle():
+    o = OracleFilter(W, H, storage="f16")
+    o.params.atrous_iterations = LEVELS
+    o.Reset()
+    outs = []
+    for planes in _frames():
+        o.set_inputs(planes)
+        o.Filter()
+        outs.append((o.FilterBuffer[0].copy(), o.HistoryLengthBuffer.copy(), o.RenderBuffer[o.PingPongInx].copy()))
+        o.EndFrame()
+    return outs
+
+
+def _worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        band = band_of(H, world, rank)
+        o = OracleFilter(W, band.local_height, storage="f16")
+        o.params.atrous_iterations = LEVELS
+        o.Reset()
+        bf = BandedFilter(o, band, ORACLE_OPS, levels=LEVELS)
+        for t, planes in enumerate(_frames()):
+            o.set_inputs({k: v[band.ly0:band.ly1] for k, v in planes.items()})
+            res = bf.Filter()
+            P = o.PingPongInx
+            sl = slice(band.loc(band.y0), band.loc(band.y1))
+            np.savez(os.path.join(tmp, f"r{rank}_f{t}.npz"), result=res[sl], history=o.HistoryLengthBuffer[sl], colour=o.RenderBuffer[P][sl])
+            bf.EndFrame()
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [2])
+def test_bands_with_halo_exchange_equal_the_whole_frame_gloo(world, tmp_path):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    want = _full_oracle()
+    for t in range(FRAMES):
+        parts = [np.load(tmp_path / f"r{r}_f{t}.npz") for r in range(world)]
+        for key, idx in (("result", 0), ("history", 1), ("colour", 2)):
+            got = np.concatenate([p[key] for p in parts], axis=0)
+            assert np.array_equal(got.view(np.uint8), want[t][idx].view(np.uint8)), f"frame {t}: {key} differs from the unpartitioned oracle"
+
+
+# ---- GPU: two bands on one device, exchanged in-process, against the unpartitioned CUDA path ------------------------
+@pytest.mark.gpu
+def test_bands_on_gpu_equal_the_whole_frame():
+    from svgf_b200 import SvgfFilter
+    from svgf_b200.bands import GPU_OPS
+    Wg, Hg, world = 256, 192, 2
+    frames = [synth.frame_host(Wg, Hg, t, vert_px=2.5) for t in range(FRAMES)]
+    full = SvgfFilter(Wg, Hg, storage="f16")
+    full.Reset()
+    bands = [band_of(Hg, world, r) for r in range(world)]
+    parts = [SvgfFilter(Wg, b.local_height, storage="f16") for b in bands]
+    for p in parts:
+        p.Reset()
+
+    def up(f, planes):
+        P = f.PingPongInx
+        f.Framebuffer[P].normal.copy_(torch.from_numpy(planes["normal"].view(np.int16)))
+        f.Framebuffer[P].uv.copy_(torch.from_numpy(planes["uv"].view(np.int16)))
+        f.Framebuffer[P].motion.copy_(torch.from_numpy(planes["motion"]))
+        f.RenderBuffer[P].copy_(torch.from_numpy(planes["colour"]))
+
+    def swap(ts, rows):
+        # the exchange of svgf_b200.bands.exchange_rows for two bands living in one process
+        a, b = bands
+        for ta, tb in ts:
+            ta[a.loc(a.y1):a.loc(a.y1 + rows)].copy_(tb[b.loc(b.y0):b.loc(b.y0 + rows)])
+            tb[b.loc(b.y0 - rows):b.loc(b.y0)].copy_(ta[a.loc(a.y1 - rows):a.loc(a.y1)])
+
+    for t, planes in enumerate(frames):
+        up(full, planes)
+        full.Filter()
+        for f, b in zip(parts, bands):
+            up(f, {k: v[b.ly0:b.ly1] for k, v in planes.items()})
+        fa, fb = parts
+        Q = 1 - fa.PingPongInx
+        if t > 0:
+            swap([(fa.RenderBuffer[Q], fb.RenderBuffer[Q]), (fa.MomentsBuffer[Q], fb.MomentsBuffer[Q]),
+                  (fa.HistoryLengthBuffer, fb.HistoryLengthBuffer)], APRON)
+        for f in parts:
+            GPU_OPS["temporal_variance"](f)
+        k = 0
+        for level in range(LEVELS):
+            swap([(fa.FilterBuffer[k], fb.FilterBuffer[k])], 2 << level)
+            for f in parts:
+                GPU_OPS["atrous_level"](f, level, f.FilterBuffer[k], f.FilterBuffer[1 - k])
+            k = 1 - k
+        torch.cuda.synchronize()
+        got = torch.cat([f.FilterBuffer[k][b.loc(b.y0):b.loc(b.y1)] for f, b in zip(parts, bands)]).cpu().numpy()
+        want = full.FilterBuffer[0].cpu().numpy()
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), f"frame {t}: banded result differs from the whole-frame CUDA path"
+        hist = torch.cat([f.HistoryLengthBuffer[b.loc(b.y0):b.loc(b.y1)] for f, b in zip(parts, bands)]).cpu().numpy()
+        assert np.array_equal(hist, full.HistoryLengthBuffer.cpu().numpy())
+        full.EndFrame()
+        for f in parts:
+            f.EndFrame()
