@@ -15,7 +15,7 @@ vertical neighbours:
     come out wrong, but they are never read for a band row before the next exchange overwrites them.
 
 The class is backend-agnostic: it drives any object with the SvgfFilter interface (svgf_b200.filter.SvgfFilter on
-a GPU; tests/oracle_lib.OracleFilter behind torch CPU views in the world_size-2 gloo test) through the three
+a GPU; the CPU checker behind torch CPU views in the world_size-2 gloo test) through the three
 callables below, so the partition / exchange logic is identical in both.
 """
 from dataclasses import dataclass
