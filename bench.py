@@ -159,6 +159,7 @@ def run_ours(args, rank, world, local):
     ring = FrameRing(W, H, R, args.storage, seed=rank, device=dev)
     f = SvgfFilter(W, H, device=dev, storage=args.storage)
     f.SpatialFilterSteps = args.levels
+    f.params.flags = args.flags
     lib = f.lib
     stream = torch.cuda.current_stream(dev)
     sptr = C.c_void_p(stream.cuda_stream)
@@ -261,10 +262,10 @@ def run_ours(args, rank, world, local):
                                + (f"; {world} independent streams, one per GPU" if world > 1 else ""),
                    "width": W, "height": H, "atrous_levels": n_levels, "storage": args.storage, "frames_resident": R,
                    "l2": "every step reads a fresh frame (%.0f MB of inputs > 126 MB L2)" % (IN_BYTES_PER_PX[args.storage] * W * H / 1e6),
-                   "params": "reference defaults (history 24, depth 0.8, normal 0.9, phi colour 10, phi normal 128)"},
+                   "params": "reference defaults (history 24, depth 0.8, normal 0.9, phi colour 10, phi normal 128)", "flags": args.flags},
         "e2e": {"value": round(e2e_value, 4), "unit": "Gpix/s", "h2d_bytes_per_step": IN_BYTES_PER_PX[args.storage] * W * H,
                 "d2h_bytes_per_step": OUT_BYTES_PER_PX[args.storage] * W * H, "ms_per_step": round(e2e_ms / Ke, 4), "steps": Ke,
-                "api": "svgf_frame_host (pinned host buffers)", "result_checksum": checksum},
+                "api": "svgf_frame_host (pinned host buffers; copy-in, kernels and copy-out of consecutive frames overlap on three streams; timed region starts with the pipeline drained)", "result_checksum": checksum},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "a-trous levels (%d launches/frame)" % at_launches,
                      "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
@@ -474,9 +475,10 @@ def main():
     ap.add_argument("--storage", default="f16", choices=["f16", "f32"])
     ap.add_argument("--levels", type=int, default=5)
     ap.add_argument("--ring", type=int, default=200, help="max distinct frames kept resident in HBM")
-    ap.add_argument("--e2e-steps", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--cpu-budget-px", type=float, default=1.6e6, help="pixels per frame of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="svgf_params.flags for A/B runs (8 = no uniform-normal tile shortcut)")
     ap.add_argument("--mode", default="streams", choices=["streams", "bands"],
                     help="multi-GPU sharding: independent frame streams per GPU (weak scaling, default) or one frame in "
                          "horizontal bands with per-level halo exchange (strong scaling; BASELINE configs[3], use --workload 8k)")

@@ -70,6 +70,10 @@ typedef enum svgf_variance_prefilter { SVGF_VARIANCE_PREFILTER_NONE = 0 } svgf_v
 #define SVGF_FLAG_NO_LEVEL_FUSION 2u
 /* Run every stage with the simple one-thread-per-pixel kernels instead of the tiled ones (A/B baseline). */
 #define SVGF_FLAG_BASIC_KERNELS 4u
+/* a-trous: do not take the uniform-normal tile shortcut (tiles whose staged texels all carry one normal vector
+ * evaluate the normal weight once per tile; results are bit-identical either way - the flag exists for A/B timing
+ * and for the parity tests that pin that identity). */
+#define SVGF_FLAG_NO_UNIFORM_TILES 8u
 
 /* Tunables.  Defaults (svgf_default_params) are the reference's members src/App.h:109-114, GUI ranges
  * src/GUI.cpp:988-993.  phi_depth / alpha_min / moments_alpha_min are additions whose defaults
@@ -178,10 +182,16 @@ int svgf_last_cuda_error(const svgf_ctx *ctx);
 /* Number of kernel launches issued through this context so far (for bench accounting). */
 uint64_t svgf_launch_count(const svgf_ctx *ctx);
 
-/* Host-buffer convenience used by the end-to-end benchmark and by callers without device memory of their
- * own: copies one frame's inputs host->device, runs svgf_frame, copies the result device->host.
- * `h_*` are pinned or pageable HOST pointers in the same texel formats; the previous frame's state stays
- * resident in the context between calls (reset=1 starts a new sequence). */
+/* Host-buffer path (what the end-to-end benchmark times, and what a caller without device memory of its own
+ * uses): one frame's inputs host->device, svgf_frame, the result device->host.  `h_*` are pinned (or pageable)
+ * HOST pointers in the same texel formats; the previous frame's state stays resident in the context between
+ * calls (reset=1 starts a new sequence).
+ * The call is asynchronous and PIPELINED across calls: inputs are staged into a 3-slot device ring on a
+ * context-owned copy-in stream, the kernels run on `stream`, the result leaves on a context-owned copy-out
+ * stream, and `stream` is made to wait for that copy - so the PCIe transfers of frames t+1 and t-1 overlap the
+ * kernels of frame t, and synchronising `stream` (or an event recorded on it after the call) guarantees that
+ * h_result / h_history_out of every earlier call are complete and that the h_* inputs may be reused.  Host inputs
+ * must stay valid and unmodified until then. */
 svgf_status svgf_frame_host(svgf_ctx *ctx, const svgf_params *params,
                             const void *h_normal_mat, const void *h_uv_inst, const void *h_motion_depth,
                             const void *h_noisy_colour, void *h_result, uint8_t *h_history_out,

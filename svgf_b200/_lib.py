@@ -11,7 +11,7 @@ SYNTH_PATH = os.path.join(_HERE, "libsvgf_synth.so")
 SVGF_OK, SVGF_INVALID_ARG, SVGF_UNSUPPORTED, SVGF_CUDA_ERROR = 0, 1, 2, 3
 SVGF_STORE_F16, SVGF_STORE_F32 = 0, 1
 SVGF_MESH_ID_INTENDED, SVGF_MESH_ID_REFERENCE_VACUOUS = 0, 1
-SVGF_FLAG_NO_GUIDE_CACHE, SVGF_FLAG_NO_LEVEL_FUSION, SVGF_FLAG_BASIC_KERNELS = 1, 2, 4
+SVGF_FLAG_NO_GUIDE_CACHE, SVGF_FLAG_NO_LEVEL_FUSION, SVGF_FLAG_BASIC_KERNELS, SVGF_FLAG_NO_UNIFORM_TILES = 1, 2, 4, 8
 SVGF_ABI_VERSION = 1
 
 

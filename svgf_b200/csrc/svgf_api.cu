@@ -34,11 +34,17 @@ struct svgf_ctx {
     static constexpr int kMaxProf = 4096;
     cudaEvent_t *prof_ev = nullptr;       // 4 events per frame
     int prof_frames = 0;
-    // device-resident state of the host-buffer path (svgf_frame_host)
+    // device-resident state of the host-buffer path (svgf_frame_host): a 3-slot ring of staged inputs filled on a
+    // copy-in stream, results drained on a copy-out stream, so that the PCIe transfers of frames t+1 and t-1
+    // overlap the kernels of frame t
     struct HostPath {
-        void *normal[2] = {nullptr, nullptr}, *uv[2] = {nullptr, nullptr}, *motion[2] = {nullptr, nullptr};
+        static constexpr int kRing = 3;
+        void *normal[kRing] = {}, *uv[kRing] = {}, *motion[kRing] = {}, *noisy[kRing] = {};
         void *render[2] = {nullptr, nullptr}, *moments[2] = {nullptr, nullptr}, *filter[2] = {nullptr, nullptr};
         uint8_t *history = nullptr;
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        cudaEvent_t ev_in[kRing] = {}, ev_done[kRing] = {}, ev_out = nullptr;
+        uint64_t frame = 0;                 // frames submitted since the ring was created
         int ping_pong = 0;
         bool ready = false;
     } hp;
@@ -332,6 +338,7 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
         ((uintptr_t)in % 16) == 0) {
         AtrousTiledArgs t;
         t.W = c->W; t.H = c->H; t.level = level; t.tiles_x = t.tiles_y = 0;
+        t.uniform_tiles = (p->flags & SVGF_FLAG_NO_UNIFORM_TILES) ? 0 : 1;
         t.kL_scale = kLog2e / p->phi_colour;
         t.kZ_scale = kLog2e / ((float)(1 << level) * p->phi_depth);
         t.k1 = a.nt.k1; t.k2 = a.nt.k2; t.k3 = a.nt.k3; t.k4 = a.nt.k4; t.k5 = a.nt.k5;
@@ -455,10 +462,15 @@ void svgf_destroy(svgf_ctx *c) {
         for (int i = 0; i < svgf_ctx::kMaxProf * 4; i++) cudaEventDestroy(c->prof_ev[i]);
         delete[] c->prof_ev;
     }
-    for (int k = 0; k < 2; k++) {
-        cudaFree(c->hp.normal[k]); cudaFree(c->hp.uv[k]); cudaFree(c->hp.motion[k]);
-        cudaFree(c->hp.render[k]); cudaFree(c->hp.moments[k]); cudaFree(c->hp.filter[k]);
+    if (c->hp.s_in) { cudaStreamSynchronize(c->hp.s_in); cudaStreamDestroy(c->hp.s_in); }
+    if (c->hp.s_out) { cudaStreamSynchronize(c->hp.s_out); cudaStreamDestroy(c->hp.s_out); }
+    for (int k = 0; k < svgf_ctx::HostPath::kRing; k++) {
+        cudaFree(c->hp.normal[k]); cudaFree(c->hp.uv[k]); cudaFree(c->hp.motion[k]); cudaFree(c->hp.noisy[k]);
+        if (c->hp.ev_in[k]) cudaEventDestroy(c->hp.ev_in[k]);
+        if (c->hp.ev_done[k]) cudaEventDestroy(c->hp.ev_done[k]);
     }
+    if (c->hp.ev_out) cudaEventDestroy(c->hp.ev_out);
+    for (int k = 0; k < 2; k++) { cudaFree(c->hp.render[k]); cudaFree(c->hp.moments[k]); cudaFree(c->hp.filter[k]); }
     cudaFree(c->hp.history);
     delete c;
 }
@@ -631,6 +643,13 @@ svgf_status svgf_profile_end(svgf_ctx *c, double stage_ms[3], int *frames) {
 }
 
 // ---- host-buffer path ----------------------------------------------------------------------------------------
+// Frame t:   copy-in stream : wait(kernels of frame t-2 done)  H2D inputs -> ring slot t%3          record ev_in[t%3]
+//            caller's stream: wait(ev_in[t%3])  noisy -> RenderBuffer[P]  svgf_frame              record ev_done[t%3]
+//                             wait(ev_out)                       (so a sync of the caller's stream covers the result)
+//            copy-out stream: wait(ev_done[t%3])  D2H result (and history)                         record ev_out
+// Slot t%3 was the *previous* G-buffer of frame t-2 (its last reader), hence the first wait.  The kernels of frame
+// t+1 are ordered after the D2H of frame t by the caller's stream itself, so FilterBuffer[0] is never overwritten
+// under the copy.  Nothing here waits for work the caller queued earlier on `stream`: the inputs are host memory.
 svgf_status svgf_frame_host(svgf_ctx *c, const svgf_params *p, const void *h_normal, const void *h_uv, const void *h_motion,
                             const void *h_colour, void *h_result, uint8_t *h_history_out, int reset, void *stream) {
     if (!c || !h_normal || !h_uv || !h_motion || !h_colour) return SVGF_INVALID_ARG;
@@ -641,16 +660,26 @@ svgf_status svgf_frame_host(svgf_ctx *c, const svgf_params *p, const void *h_nor
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)c->W * c->H;
     svgf_ctx::HostPath &hp = c->hp;
+    constexpr int R = svgf_ctx::HostPath::kRing;
     if (!hp.ready) {
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < R; k++) {
             SVGF_CUDA(c, cudaMalloc(&hp.normal[k], n * 8));
             SVGF_CUDA(c, cudaMalloc(&hp.uv[k], n * 8));
             SVGF_CUDA(c, cudaMalloc(&hp.motion[k], n * 16));
+            SVGF_CUDA(c, cudaMalloc(&hp.noisy[k], colour_bytes(c)));
+            SVGF_CUDA(c, cudaEventCreateWithFlags(&hp.ev_in[k], cudaEventDisableTiming));
+            SVGF_CUDA(c, cudaEventCreateWithFlags(&hp.ev_done[k], cudaEventDisableTiming));
+        }
+        for (int k = 0; k < 2; k++) {
             SVGF_CUDA(c, cudaMalloc(&hp.render[k], colour_bytes(c)));
             SVGF_CUDA(c, cudaMalloc(&hp.moments[k], moments_bytes(c)));
             SVGF_CUDA(c, cudaMalloc(&hp.filter[k], colour_bytes(c)));
         }
         SVGF_CUDA(c, cudaMalloc(&hp.history, n));
+        SVGF_CUDA(c, cudaEventCreateWithFlags(&hp.ev_out, cudaEventDisableTiming));
+        SVGF_CUDA(c, cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+        SVGF_CUDA(c, cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+        hp.frame = 0;
         hp.ready = true;
         reset = 1;
     }
@@ -661,26 +690,46 @@ svgf_status svgf_frame_host(svgf_ctx *c, const svgf_params *p, const void *h_nor
         hp.ping_pong = 0;
         if ((st = svgf_reset(c, &b, s))) return st;
     }
+    const uint64_t t = hp.frame;
+    const int k = (int)(t % R), kprev = (int)((t + R - 1) % R);
     const int P = hp.ping_pong;
     b.ping_pong = P;
-    SVGF_CUDA(c, cudaMemcpyAsync(hp.normal[P], h_normal, n * 8, cudaMemcpyHostToDevice, s));
-    SVGF_CUDA(c, cudaMemcpyAsync(hp.uv[P], h_uv, n * 8, cudaMemcpyHostToDevice, s));
-    SVGF_CUDA(c, cudaMemcpyAsync(hp.motion[P], h_motion, n * 16, cudaMemcpyHostToDevice, s));
-    SVGF_CUDA(c, cudaMemcpyAsync(hp.render[P], h_colour, colour_bytes(c), cudaMemcpyHostToDevice, s));
+
+    // copy-in
+    if (t >= 2) SVGF_CUDA(c, cudaStreamWaitEvent(hp.s_in, hp.ev_done[(t - 2) % R], 0));
+    SVGF_CUDA(c, cudaMemcpyAsync(hp.normal[k], h_normal, n * 8, cudaMemcpyHostToDevice, hp.s_in));
+    SVGF_CUDA(c, cudaMemcpyAsync(hp.uv[k], h_uv, n * 8, cudaMemcpyHostToDevice, hp.s_in));
+    SVGF_CUDA(c, cudaMemcpyAsync(hp.motion[k], h_motion, n * 16, cudaMemcpyHostToDevice, hp.s_in));
+    SVGF_CUDA(c, cudaMemcpyAsync(hp.noisy[k], h_colour, colour_bytes(c), cudaMemcpyHostToDevice, hp.s_in));
+    SVGF_CUDA(c, cudaEventRecord(hp.ev_in[k], hp.s_in));
+
+    // kernels, on the caller's stream
+    SVGF_CUDA(c, cudaStreamWaitEvent(s, hp.ev_in[k], 0));
+    SVGF_CUDA(c, cudaMemcpyAsync(hp.render[P], hp.noisy[k], colour_bytes(c), cudaMemcpyDeviceToDevice, s));
     svgf_gbuffer g[2];
-    for (int k = 0; k < 2; k++) {
-        g[k].position_id = nullptr; g[k].position_pitch = 0;
-        g[k].normal_mat = hp.normal[k]; g[k].normal_pitch = 0;
-        g[k].uv_inst = hp.uv[k]; g[k].uv_pitch = 0;
-        g[k].motion_depth = hp.motion[k]; g[k].motion_pitch = 0;
+    const int slot_of[2] = {P == 0 ? k : kprev, P == 0 ? kprev : k};   // g[P] = this frame's slot, g[1-P] = last frame's
+    for (int q = 0; q < 2; q++) {
+        g[q].position_id = nullptr; g[q].position_pitch = 0;
+        g[q].normal_mat = hp.normal[slot_of[q]]; g[q].normal_pitch = 0;
+        g[q].uv_inst = hp.uv[slot_of[q]]; g[q].uv_pitch = 0;
+        g[q].motion_depth = hp.motion[slot_of[q]]; g[q].motion_pitch = 0;
     }
-    // the G-buffer contents of slot P have just changed under the same pointer
-    for (int k = 0; k < 2; k++)
-        if (c->guide_key[k] == hp.motion[P]) c->guide_key[k] = nullptr;
+    // the contents of ring slot k have just changed under the same pointer
+    for (int q = 0; q < 2; q++)
+        if (c->guide_key[q] == hp.motion[k]) c->guide_key[q] = nullptr;
     if ((st = svgf_frame(c, p, g, &b, s))) return st;
-    if (h_result) SVGF_CUDA(c, cudaMemcpyAsync(h_result, hp.filter[0], colour_bytes(c), cudaMemcpyDeviceToHost, s));
-    if (h_history_out) SVGF_CUDA(c, cudaMemcpyAsync(h_history_out, hp.history, n, cudaMemcpyDeviceToHost, s));
+    SVGF_CUDA(c, cudaEventRecord(hp.ev_done[k], s));
+
+    // copy-out
+    if (h_result || h_history_out) {
+        SVGF_CUDA(c, cudaStreamWaitEvent(hp.s_out, hp.ev_done[k], 0));
+        if (h_result) SVGF_CUDA(c, cudaMemcpyAsync(h_result, hp.filter[0], colour_bytes(c), cudaMemcpyDeviceToHost, hp.s_out));
+        if (h_history_out) SVGF_CUDA(c, cudaMemcpyAsync(h_history_out, hp.history, n, cudaMemcpyDeviceToHost, hp.s_out));
+        SVGF_CUDA(c, cudaEventRecord(hp.ev_out, hp.s_out));
+        SVGF_CUDA(c, cudaStreamWaitEvent(s, hp.ev_out, 0));
+    }
     hp.ping_pong = 1 - P;
+    hp.frame = t + 1;
     return SVGF_OK;
 }
 

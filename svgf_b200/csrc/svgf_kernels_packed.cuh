@@ -47,29 +47,50 @@ struct PkAcc { float2 S, r, g, b, v; };
 struct PkTap { float2 r, g, b, v, l, z, nx, ny, nz; };
 struct PkCoef { float k1, k2, k3, k4, k5; };
 
-// one tap for both outputs of the pair; ck = -log2(kernel weight), cinv = 1/length(xx,yy)
-template <int TERMS>
-__device__ __forceinline__ void pk_tap2(PkAcc &A, const PkCentre &C, const PkTap &q, float ck, float cinv, const PkCoef &k) {
+// one tap for both outputs of the pair; ck = -log2(kernel weight), cinv = 1/length(xx,yy).
+// UNIF: every normal the tile can see is the same vector (see the kernel), so u = 1 - sat(n.n) and the series value p
+// are two tile constants (un, pn) and the dot product, the clamp and the series drop out of the tap; the exponent is
+// still formed by the same single fma(-u, p, -base), so the weight has the same bits as in the general form.
+template <int TERMS, bool UNIF = false>
+__device__ __forceinline__ void pk_tap2(PkAcc &A, const PkCentre &C, const PkTap &q, float ck, float cinv, const PkCoef &k,
+                                        float un = 0.f, float pn = 0.f) {
     float2 base = __ffma2_rn(f2abs(__fadd2_rn(q.l, f2neg(C.lc))), C.kL, f2bc(ck));
     const float2 tz = __fmul2_rn(f2abs(__fadd2_rn(q.z, f2neg(C.zc))), C.kZ);
     base = __ffma2_rn(tz, f2bc(cinv), base);
-    float2 d = __fmul2_rn(C.nx, q.nx);                      // (x*x' + y*y') + z*z', reference dot order
-    d = __ffma2_rn(C.ny, q.ny, d);
-    d = __ffma2_rn(C.nz, q.nz, d);
-    float2 u = __fadd2_rn(f2bc(1.0f), f2neg(d));
-    u = make_float2(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));    // d > 1 saturates to 1 (u = 0); d < 0 gives u > 1: weight ~ 2^-96
-    float2 p;
-    if (TERMS == 5) { p = __ffma2_rn(u, f2bc(k.k5), f2bc(k.k4)); p = __ffma2_rn(u, p, f2bc(k.k3)); }
-    else p = __ffma2_rn(u, f2bc(k.k4), f2bc(k.k3));
-    p = __ffma2_rn(u, p, f2bc(k.k2));
-    p = __ffma2_rn(u, p, f2bc(k.k1));
-    const float2 e = __ffma2_rn(f2neg(u), p, f2neg(base));
+    float2 e;
+    if (UNIF) {
+        e = __ffma2_rn(f2bc(-un), f2bc(pn), f2neg(base));
+    } else {
+        float2 d = __fmul2_rn(C.nx, q.nx);                      // (x*x' + y*y') + z*z', reference dot order
+        d = __ffma2_rn(C.ny, q.ny, d);
+        d = __ffma2_rn(C.nz, q.nz, d);
+        float2 u = __fadd2_rn(f2bc(1.0f), f2neg(d));
+        u = make_float2(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));    // d > 1 saturates to 1 (u = 0); d < 0 gives u > 1: weight ~ 2^-96
+        float2 p;
+        if (TERMS == 5) { p = __ffma2_rn(u, f2bc(k.k5), f2bc(k.k4)); p = __ffma2_rn(u, p, f2bc(k.k3)); }
+        else p = __ffma2_rn(u, f2bc(k.k4), f2bc(k.k3));
+        p = __ffma2_rn(u, p, f2bc(k.k2));
+        p = __ffma2_rn(u, p, f2bc(k.k1));
+        e = __ffma2_rn(f2neg(u), p, f2neg(base));
+    }
     const float2 w = make_float2(fast_exp2(e.x), fast_exp2(e.y));
     A.S = __fadd2_rn(A.S, w);
     A.r = __ffma2_rn(w, q.r, A.r);
     A.g = __ffma2_rn(w, q.g, A.g);
     A.b = __ffma2_rn(w, q.b, A.b);
     A.v = __ffma2_rn(__fmul2_rn(w, w), q.v, A.v);
+}
+
+// u and p of one normal pair, scalar, same operations and roundings as the packed tap (and as pk_tap1)
+template <int TERMS>
+__device__ __forceinline__ void pk_normal_term(float nx, float ny, float nz, float qnx, float qny, float qnz, const PkCoef &k,
+                                               float &u, float &p) {
+    const float d = fmaf(nz, qnz, fmaf(ny, qny, nx * qnx));
+    u = fmaxf(1.0f - d, 0.0f);
+    if (TERMS == 5) { p = fmaf(u, k.k5, k.k4); p = fmaf(u, p, k.k3); }
+    else p = fmaf(u, k.k4, k.k3);
+    p = fmaf(u, p, k.k2);
+    p = fmaf(u, p, k.k1);
 }
 
 // same tap with the centre's luminance and depth stored NEGATED (nlc = -lc, nzc = -zc): inside a rolled loop the
@@ -100,19 +121,15 @@ __device__ __forceinline__ void pk_tap2n(PkAcc &A, const PkCentreN &C, const PkT
 }
 
 // scalar form for one output and one tap (level 0, odd dx)
-template <int TERMS>
+template <int TERMS, bool UNIF = false>
 __device__ __forceinline__ void pk_tap1(float &S, float &Ar, float &Ag, float &Ab, float &Av, float lc, float zc, float nx, float ny,
                                         float nz, float kL, float kZ, float ql, float qz, float qnx, float qny, float qnz, float qr,
-                                        float qg, float qb, float qv, float ck, float cinv, const PkCoef &k) {
+                                        float qg, float qb, float qv, float ck, float cinv, const PkCoef &k, float un = 0.f,
+                                        float pn = 0.f) {
     float base = fmaf(fabsf(ql - lc), kL, ck);
     base = fmaf(fabsf(qz - zc) * kZ, cinv, base);
-    const float d = fmaf(nz, qnz, fmaf(ny, qny, nx * qnx));
-    const float u = fmaxf(1.0f - d, 0.0f);
-    float p;
-    if (TERMS == 5) { p = fmaf(u, k.k5, k.k4); p = fmaf(u, p, k.k3); }
-    else p = fmaf(u, k.k4, k.k3);
-    p = fmaf(u, p, k.k2);
-    p = fmaf(u, p, k.k1);
+    float u = un, p = pn;
+    if (!UNIF) pk_normal_term<TERMS>(nx, ny, nz, qnx, qny, qnz, k, u, p);
     const float w = fast_exp2(fmaf(-u, p, -base));
     S += w;
     Ar = fmaf(w, qr, Ar); Ag = fmaf(w, qg, Ag); Ab = fmaf(w, qb, Ab);
@@ -122,6 +139,75 @@ __device__ __forceinline__ void pk_tap1(float &S, float &Ar, float &Ag, float &A
 __device__ __forceinline__ constexpr float tap_inv_len(int ax, int ay) {
     const int l2 = ax * ax + ay * ay;   // 1 2 4 5 8
     return l2 == 1 ? 1.0f : l2 == 2 ? 0.70710678f : l2 == 4 ? 0.5f : l2 == 5 ? 0.44721360f : 0.35355339f;
+}
+
+// all 24 taps of the kPkRows outputs of one thread (both pixels of the pair)
+template <int STEP, int TERMS, bool UNIF>
+__device__ __forceinline__ void pk_all_taps(PkAcc (&A)[kPkRows], const PkCentre (&C)[kPkRows], const float4 *sC0, const float4 *sC1,
+                                            const float4 *sG0, const float4 *sG1, const float2 *sL, int row0, int pcol,
+                                            const PkCoef &k, float un, float pn) {
+    using G = PackedGeom<STEP>;
+    if (STEP > 1) {
+#pragma unroll
+        for (int dx = -2; dx <= 2; dx++) {
+#pragma unroll
+            for (int t = -2; t < kPkRows + 2; t++) {
+                const int si = (row0 + t) * G::pairs + pcol + dx * (STEP / 2);
+                const float4 c0 = sC0[si], c1 = sC1[si];
+                float4 g0, g1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (UNIF) { const float2 zz = *reinterpret_cast<const float2 *>(&sG0[si]); g0 = make_float4(zz.x, zz.y, 0.f, 0.f); }
+                else { g0 = sG0[si]; g1 = sG1[si]; }
+                PkTap q;
+                q.r = make_float2(c0.x, c0.y); q.g = make_float2(c0.z, c0.w); q.b = make_float2(c1.x, c1.y); q.v = make_float2(c1.z, c1.w);
+                q.z = make_float2(g0.x, g0.y); q.nx = make_float2(g0.z, g0.w); q.ny = make_float2(g1.x, g1.y); q.nz = make_float2(g1.z, g1.w);
+                q.l = sL[si];
+#pragma unroll
+                for (int j = 0; j < kPkRows; j++) {
+                    const int dy = t - j;
+                    if (dy < -2 || dy > 2 || (dx == 0 && dy == 0)) continue;
+                    const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
+                    pk_tap2<TERMS, UNIF>(A[j], C[j], q, tap_neg_log2_kernel(ax, ay), tap_inv_len(ax, ay), k, un, pn);
+                }
+            }
+        }
+    } else {
+        // level 0: the six columns x-2 .. x+3 are the three aligned pairs m = -1, 0, +1.  Pair m serves dx = 2m packed
+        // (outputs x and x+1 tap columns x+2m and x+1+2m) and the odd offsets on its halves: output 0 (column x)
+        // taps x-1 = pair(-1).hi and x+1 = pair(0).hi; output 1 (column x+1) taps x = pair(0).lo and x+2 = pair(+1).lo.
+        // One pair is live at a time.
+#pragma unroll
+        for (int t = -2; t < kPkRows + 2; t++) {
+#pragma unroll
+            for (int m = -1; m <= 1; m++) {
+                const int si = (row0 + t) * G::pairs + pcol + m;
+                const float4 c0 = sC0[si], c1 = sC1[si];
+                float4 g0, g1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (UNIF) { const float2 zz = *reinterpret_cast<const float2 *>(&sG0[si]); g0 = make_float4(zz.x, zz.y, 0.f, 0.f); }
+                else { g0 = sG0[si]; g1 = sG1[si]; }
+                PkTap q;
+                q.r = make_float2(c0.x, c0.y); q.g = make_float2(c0.z, c0.w); q.b = make_float2(c1.x, c1.y); q.v = make_float2(c1.z, c1.w);
+                q.z = make_float2(g0.x, g0.y); q.nx = make_float2(g0.z, g0.w); q.ny = make_float2(g1.x, g1.y); q.nz = make_float2(g1.z, g1.w);
+                q.l = sL[si];
+#pragma unroll
+                for (int j = 0; j < kPkRows; j++) {
+                    const int dy = t - j;
+                    if (dy < -2 || dy > 2) continue;
+                    const int ay = dy < 0 ? -dy : dy;
+                    if (!(m == 0 && dy == 0))
+                        pk_tap2<TERMS, UNIF>(A[j], C[j], q, tap_neg_log2_kernel(m == 0 ? 0 : 2, ay), tap_inv_len(m == 0 ? 0 : 2, ay), k, un, pn);
+                    const float ck = tap_neg_log2_kernel(1, ay), ci = tap_inv_len(1, ay);
+                    if (m <= 0)   // output 0 <- this pair's hi half (x-1 for m = -1, x+1 for m = 0)
+                        pk_tap1<TERMS, UNIF>(A[j].S.x, A[j].r.x, A[j].g.x, A[j].b.x, A[j].v.x, C[j].lc.x, C[j].zc.x, C[j].nx.x, C[j].ny.x,
+                                       C[j].nz.x, C[j].kL.x, C[j].kZ.x, q.l.y, q.z.y, q.nx.y, q.ny.y, q.nz.y, q.r.y, q.g.y, q.b.y, q.v.y,
+                                       ck, ci, k, un, pn);
+                    if (m >= 0)   // output 1 <- this pair's lo half (x for m = 0, x+2 for m = +1)
+                        pk_tap1<TERMS, UNIF>(A[j].S.y, A[j].r.y, A[j].g.y, A[j].b.y, A[j].v.y, C[j].lc.y, C[j].zc.y, C[j].nx.y, C[j].ny.y,
+                                       C[j].nz.y, C[j].kL.y, C[j].kZ.y, q.l.x, q.z.x, q.nx.x, q.ny.x, q.nz.x, q.r.x, q.g.x, q.b.x, q.v.x,
+                                       ck, ci, k, un, pn);
+                }
+            }
+        }
+    }
 }
 
 template <bool F32, int STEP, int TERMS>
@@ -144,6 +230,13 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     const int y0 = yblock * (G::tile_rows * STEP) + phase;
 
     // ---- stage the tile, one pixel pair per thread and iteration; all global loads first ----
+    // Uniform-normal tiles: when every in-image texel the tile stages (halo included) carries the same non-zero
+    // normal as the tile's first pixel - any planar surface: floors, walls, box faces - the normal weight of all
+    // 24 x 1536 (centre, tap) pairs is one number, and the taps run the UNIF form (12 instead of 19 packed
+    // operations, no normal loads).  Compared as floats: equal values give equal dot products (+0 == -0 included),
+    // NaN never matches.  Texels outside the image are excluded: their weight is 0 through z = +inf either way.
+    const float4 nref = __ldg(guide_n + (size_t)min(y0, a.H - 1) * a.W + x0);
+    bool same_n = a.uniform_tiles && (nref.y != 0.0f || nref.z != 0.0f || nref.w != 0.0f);
     constexpr int kIters = (G::npairs + kPkThreads - 1) / kPkThreads;
     CT rc0[kIters], rc1[kIters];
     float4 rg0[kIters], rg1[kIters];
@@ -166,6 +259,8 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
             }
             rg0[i] = __ldg(guide_n + gi);
             rg1[i] = __ldg(guide_n + gi + 1);
+            same_n &= (rg0[i].y == nref.y) & (rg0[i].z == nref.z) & (rg0[i].w == nref.w) & (rg1[i].y == nref.y) & (rg1[i].z == nref.z) &
+                      (rg1[i].w == nref.w);
         }
     }
 #pragma unroll
@@ -182,7 +277,7 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
             sL[idx] = make_float2(luminance(r0, g0, b0), luminance(r1, g1, b1));
         }
     }
-    __syncthreads();
+    const bool uniform_n = __syncthreads_and(same_n) != 0;
 
     const int pcx = tid & (kPkPairs - 1), tg = tid / kPkPairs;
     const int gx = x0 + 2 * pcx;
@@ -190,6 +285,8 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     const int row0 = tg * kPkRows + 2;
     PkCoef k;
     k.k1 = a.k1; k.k2 = a.k2; k.k3 = a.k3; k.k4 = a.k4; k.k5 = a.k5;
+    float un, pn;
+    pk_normal_term<TERMS>(nref.y, nref.z, nref.w, nref.y, nref.z, nref.w, k, un, pn);
 
     PkCentre C[kPkRows];
     PkAcc A[kPkRows];
@@ -217,61 +314,8 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     }
 
     if (__any_sync(0xffffffffu, any_live)) {
-        if (STEP > 1) {
-#pragma unroll
-            for (int dx = -2; dx <= 2; dx++) {
-#pragma unroll
-                for (int t = -2; t < kPkRows + 2; t++) {
-                    const int si = (row0 + t) * G::pairs + pcol + dx * (STEP / 2);
-                    const float4 c0 = sC0[si], c1 = sC1[si], g0 = sG0[si], g1 = sG1[si];
-                    PkTap q;
-                    q.r = make_float2(c0.x, c0.y); q.g = make_float2(c0.z, c0.w); q.b = make_float2(c1.x, c1.y); q.v = make_float2(c1.z, c1.w);
-                    q.z = make_float2(g0.x, g0.y); q.nx = make_float2(g0.z, g0.w); q.ny = make_float2(g1.x, g1.y); q.nz = make_float2(g1.z, g1.w);
-                    q.l = sL[si];
-#pragma unroll
-                    for (int j = 0; j < kPkRows; j++) {
-                        const int dy = t - j;
-                        if (dy < -2 || dy > 2 || (dx == 0 && dy == 0)) continue;
-                        const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
-                        pk_tap2<TERMS>(A[j], C[j], q, tap_neg_log2_kernel(ax, ay), tap_inv_len(ax, ay), k);
-                    }
-                }
-            }
-        } else {
-            // level 0: the six columns x-2 .. x+3 are the three aligned pairs m = -1, 0, +1.  Pair m serves dx = 2m packed
-            // (outputs x and x+1 tap columns x+2m and x+1+2m) and the odd offsets on its halves: output 0 (column x)
-            // taps x-1 = pair(-1).hi and x+1 = pair(0).hi; output 1 (column x+1) taps x = pair(0).lo and x+2 = pair(+1).lo.
-            // One pair is live at a time.
-#pragma unroll
-            for (int t = -2; t < kPkRows + 2; t++) {
-#pragma unroll
-                for (int m = -1; m <= 1; m++) {
-                    const int si = (row0 + t) * G::pairs + pcol + m;
-                    const float4 c0 = sC0[si], c1 = sC1[si], g0 = sG0[si], g1 = sG1[si];
-                    PkTap q;
-                    q.r = make_float2(c0.x, c0.y); q.g = make_float2(c0.z, c0.w); q.b = make_float2(c1.x, c1.y); q.v = make_float2(c1.z, c1.w);
-                    q.z = make_float2(g0.x, g0.y); q.nx = make_float2(g0.z, g0.w); q.ny = make_float2(g1.x, g1.y); q.nz = make_float2(g1.z, g1.w);
-                    q.l = sL[si];
-#pragma unroll
-                    for (int j = 0; j < kPkRows; j++) {
-                        const int dy = t - j;
-                        if (dy < -2 || dy > 2) continue;
-                        const int ay = dy < 0 ? -dy : dy;
-                        if (!(m == 0 && dy == 0))
-                            pk_tap2<TERMS>(A[j], C[j], q, tap_neg_log2_kernel(m == 0 ? 0 : 2, ay), tap_inv_len(m == 0 ? 0 : 2, ay), k);
-                        const float ck = tap_neg_log2_kernel(1, ay), ci = tap_inv_len(1, ay);
-                        if (m <= 0)   // output 0 <- this pair's hi half (x-1 for m = -1, x+1 for m = 0)
-                            pk_tap1<TERMS>(A[j].S.x, A[j].r.x, A[j].g.x, A[j].b.x, A[j].v.x, C[j].lc.x, C[j].zc.x, C[j].nx.x, C[j].ny.x,
-                                           C[j].nz.x, C[j].kL.x, C[j].kZ.x, q.l.y, q.z.y, q.nx.y, q.ny.y, q.nz.y, q.r.y, q.g.y, q.b.y, q.v.y,
-                                           ck, ci, k);
-                        if (m >= 0)   // output 1 <- this pair's lo half (x for m = 0, x+2 for m = +1)
-                            pk_tap1<TERMS>(A[j].S.y, A[j].r.y, A[j].g.y, A[j].b.y, A[j].v.y, C[j].lc.y, C[j].zc.y, C[j].nx.y, C[j].ny.y,
-                                           C[j].nz.y, C[j].kL.y, C[j].kZ.y, q.l.x, q.z.x, q.nx.x, q.ny.x, q.nz.x, q.r.x, q.g.x, q.b.x, q.v.x,
-                                           ck, ci, k);
-                    }
-                }
-            }
-        }
+        if (uniform_n) pk_all_taps<STEP, TERMS, true>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, un, pn);
+        else pk_all_taps<STEP, TERMS, false>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, 0.f, 0.f);
     }
 
     // ---- normalise and store both pixels of the pair (:615-622) ----

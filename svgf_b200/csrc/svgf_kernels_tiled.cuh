@@ -47,6 +47,7 @@ struct AtrousTiledArgs {
     float k1, k2, k3, k4, k5;   // normal term series coefficients (make_normal_term)
     int level;
     int tiles_x, tiles_y;       // tiles_y counts (row block, phase) pairs
+    int uniform_tiles;          // packed kernel: allow the uniform-normal tile shortcut
 };
 
 // -log2 of the reference's tap kernel KW[|xx|] * KW[|yy|], KW = {1, 2/3, 1/6} as floats (src/Filter.cuh:540,582):
