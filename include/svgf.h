@@ -68,6 +68,11 @@ typedef enum svgf_variance_prefilter { SVGF_VARIANCE_PREFILTER_NONE = 0 } svgf_v
 #define SVGF_FLAG_NO_GUIDE_CACHE 1u
 /* svgf_frame / svgf_atrous: run every a-trous level as its own launch (disables two-level fusion). */
 #define SVGF_FLAG_NO_LEVEL_FUSION 2u
+/* svgf_frame / svgf_atrous: run a-trous levels 0 and 1 as ONE launch with the level-0 result kept in shared memory
+ * (BASELINE configs[2] "two-level-fused" variant).  Results are bit-identical to two launches.  Off by default: the
+ * level is bound by arithmetic, not HBM, and the fused tile evaluates level 0 1.5 x redundantly on its apron - measured
+ * slower on B200.  SVGF_FLAG_NO_LEVEL_FUSION overrides it. */
+#define SVGF_FLAG_FUSE_LEVELS_01 16u
 /* Run every stage with the simple one-thread-per-pixel kernels instead of the tiled ones (A/B baseline). */
 #define SVGF_FLAG_BASIC_KERNELS 4u
 /* a-trous: do not take the uniform-normal tile shortcut (tiles whose staged texels all carry one normal vector

@@ -12,6 +12,7 @@ SVGF_OK, SVGF_INVALID_ARG, SVGF_UNSUPPORTED, SVGF_CUDA_ERROR = 0, 1, 2, 3
 SVGF_STORE_F16, SVGF_STORE_F32 = 0, 1
 SVGF_MESH_ID_INTENDED, SVGF_MESH_ID_REFERENCE_VACUOUS = 0, 1
 SVGF_FLAG_NO_GUIDE_CACHE, SVGF_FLAG_NO_LEVEL_FUSION, SVGF_FLAG_BASIC_KERNELS, SVGF_FLAG_NO_UNIFORM_TILES = 1, 2, 4, 8
+SVGF_FLAG_FUSE_LEVELS_01 = 16
 SVGF_ABI_VERSION = 1
 
 

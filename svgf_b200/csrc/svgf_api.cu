@@ -12,6 +12,7 @@
 #include "svgf_kernels_tiled.cuh"
 #include "svgf_kernels_packed.cuh"
 #include "svgf_kernels_stream.cuh"
+#include "svgf_kernels_fused.cuh"
 #include <cstdlib>
 
 using namespace svgf;
@@ -326,6 +327,49 @@ svgf_status dispatch_atrous_tiled(svgf_ctx *c, const AtrousTiledArgs &a, int gui
     return SVGF_UNSUPPORTED;
 }
 
+// Levels 0 and 1 in one launch (svgf_kernels_fused.cuh).  Same preconditions as the packed single-level kernel.
+template <bool F32>
+bool fused01_applicable(const svgf_ctx *c, const svgf_params *p, const void *in, const void *out, const void *hist_colour) {
+    const NormalTerm nt = make_normal_term(p->phi_normal);
+    return (p->flags & SVGF_FLAG_FUSE_LEVELS_01) && !(p->flags & (SVGF_FLAG_BASIC_KERNELS | SVGF_FLAG_NO_LEVEL_FUSION)) && nt.series &&
+           p->phi_depth > 0.0f && c->W % 2 == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 &&
+           (!hist_colour || ((uintptr_t)hist_colour % 16) == 0);
+}
+template <bool F32, int TERMS>
+svgf_status launch_atrous_fused01_t(svgf_ctx *c, const AtrousTiledArgs &t, int guide_slot, const void *in, void *out, void *hist_colour,
+                                    cudaStream_t s) {
+    using CT = typename ColourPlane<F32>::texel;
+    auto kern = atrous_fused01_kernel<F32, TERMS>;
+    static bool configured[16] = {};
+    if (!configured[c->device & 15]) {
+        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedGeom::smem_bytes));
+        configured[c->device & 15] = true;
+    }
+    const dim3 grid((c->W + kFzW - 1) / kFzW, (c->H + kFzH - 1) / kFzH);
+    kern<<<grid, kFzThreads, FusedGeom::smem_bytes, s>>>(t, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in, (CT *)out,
+                                                         (CT *)hist_colour);
+    c->launches++;
+    SVGF_CUDA(c, cudaGetLastError());
+    return SVGF_OK;
+}
+template <bool F32>
+svgf_status launch_atrous_fused01(svgf_ctx *c, const svgf_params *p, int guide_slot, const void *in, void *out, void *hist_colour,
+                                  cudaStream_t s) {
+    const SpatialArgs a = spatial_args(c, p, 0);
+    AtrousTiledArgs t;
+    t.W = c->W; t.H = c->H; t.level = 0; t.tiles_x = t.tiles_y = 0;
+    t.uniform_tiles = (p->flags & SVGF_FLAG_NO_UNIFORM_TILES) ? 0 : 1;
+    t.kL_scale = kLog2e / p->phi_colour;
+    t.kZ_scale = kLog2e / p->phi_depth;        // level 0; the kernel halves it for level 1
+    t.k1 = a.nt.k1; t.k2 = a.nt.k2; t.k3 = a.nt.k3; t.k4 = a.nt.k4; t.k5 = a.nt.k5;
+    if (p->phi_normal >= 100.0f) {             // same series selection as the single-level packed dispatch
+        const NormalTerm e3 = economised_series3(p->phi_normal);
+        t.k1 = e3.k1; t.k2 = e3.k2; t.k3 = e3.k3;
+        return launch_atrous_fused01_t<F32, 3>(c, t, guide_slot, in, out, hist_colour, s);
+    }
+    return launch_atrous_fused01_t<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);
+}
+
 template <bool F32>
 svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slot, const void *in, void *out,
                                 void *hist_colour, int level, cudaStream_t s) {
@@ -354,9 +398,17 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
         if (want_stream && pair_ok)
             return (p->phi_normal >= 100.0f) ? dispatch_atrous_stream<F32, 4>(c, t, guide_slot, in, out, hist_colour, s)
                                              : dispatch_atrous_stream<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);
-        if (!want_bulk && c->W % 2 == 0 && ((uintptr_t)out % 16) == 0 && (!hist_colour || ((uintptr_t)hist_colour % 16) == 0))
+        if (!want_bulk && c->W % 2 == 0 && ((uintptr_t)out % 16) == 0 && (!hist_colour || ((uintptr_t)hist_colour % 16) == 0)) {
+            if (p->phi_normal >= 100.0f && !(variant && !strcmp(variant, "taylor4"))) {
+                // three-term economised series (svgf_device.cuh, economised_series3): one Horner step fewer per tap,
+                // weight error <= 0.56 / (phiN log2e)^3 <= 1.9e-7 absolute
+                const NormalTerm e3 = economised_series3(p->phi_normal);
+                t.k1 = e3.k1; t.k2 = e3.k2; t.k3 = e3.k3;
+                return dispatch_atrous_packed<F32, 3>(c, t, guide_slot, in, out, hist_colour, s);
+            }
             return (p->phi_normal >= 100.0f) ? dispatch_atrous_packed<F32, 4>(c, t, guide_slot, in, out, hist_colour, s)
                                              : dispatch_atrous_packed<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);
+        }
         return (p->phi_normal >= 100.0f) ? dispatch_atrous_tiled<F32, 4>(c, t, guide_slot, in, out, hist_colour, s)
                                          : dispatch_atrous_tiled<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);
     }
@@ -369,10 +421,28 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
     return SVGF_OK;
 }
 
+// Number of buffer swaps run_atrous makes for levels first..first+n-1: one per launch (n, or n - 1 when levels 0 and 1
+// go out as one fused launch).  svgf_frame needs it up front to aim the variance output so that the result lands in
+// filter[0].
+int atrous_hops(const svgf_ctx *c, const svgf_params *p, const void *a, const void *b, const void *hist_colour, int first, int n) {
+    const bool fuse = first == 0 && n >= 2 &&
+                      (c->storage == SVGF_STORE_F32 ? fused01_applicable<true>(c, p, a, b, hist_colour)
+                                                    : fused01_applicable<false>(c, p, a, b, hist_colour));
+    return fuse ? n - 1 : n;
+}
+
 // Levels first..first+n-1, ping-ponging a -> b -> a ...; *result = last output (or `a` when n == 0).
 svgf_status run_atrous(svgf_ctx *c, const svgf_params *p, int guide_slot, void *a, void *b, void *hist_colour, int first,
                        int n, void **result, cudaStream_t s) {
     void *in = a, *out = b;
+    const bool f32 = c->storage == SVGF_STORE_F32;
+    if (first == 0 && n >= 2 && atrous_hops(c, p, a, b, hist_colour, first, n) == n - 1) {
+        svgf_status st = f32 ? launch_atrous_fused01<true>(c, p, guide_slot, in, out, hist_colour, s)
+                             : launch_atrous_fused01<false>(c, p, guide_slot, in, out, hist_colour, s);
+        if (st) return st;
+        void *t = in; in = out; out = t;
+        first = 2; n -= 2;
+    }
     for (int l = first; l < first + n; l++) {
         svgf_status st = (c->storage == SVGF_STORE_F32) ? launch_atrous_level<true>(c, p, guide_slot, in, out, hist_colour, l, s)
                                                         : launch_atrous_level<false>(c, p, guide_slot, in, out, hist_colour, l, s);
@@ -574,12 +644,13 @@ svgf_status svgf_frame(svgf_ctx *c, const svgf_params *p, const svgf_gbuffer gbu
     const bool f32 = (c->storage == SVGF_STORE_F32);
 
     const int N = p->atrous_iterations;
-    void *v_out = b->filter[N & 1], *other = b->filter[1 - (N & 1)];
+    const int hops = atrous_hops(c, p, b->filter[0], b->filter[1], b->render[P], 0, N);
+    void *v_out = b->filter[hops & 1], *other = b->filter[1 - (hops & 1)];
     const bool basic = (p->flags & SVGF_FLAG_BASIC_KERNELS) != 0;
     prof_mark(c, 0, s);
     // temporal: reads the caller-visible history plane (previous frame), writes the shadow plane.  Fused form: it
     // also writes the variance pass's output for every pixel that pass only copies or zeroes and queues the
-    // short-history pixels; -> filter[N & 1] so that N ping-pong levels end in filter[0] (the reference copies
+    // short-history pixels; -> filter[hops & 1] so that the ping-pong launches end in filter[0] (the reference copies
     // instead, src/App.cu:510-513).
     st = f32 ? launch_temporal<true>(c, p, &gbuf[P], &gbuf[Q], b->render[Q], b->render[P], b->history, c->hist_shadow,
                                      b->moments[P], b->moments[Q], basic ? nullptr : v_out, s)

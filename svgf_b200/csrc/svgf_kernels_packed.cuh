@@ -67,9 +67,9 @@ __device__ __forceinline__ void pk_tap2(PkAcc &A, const PkCentre &C, const PkTap
         float2 u = __fadd2_rn(f2bc(1.0f), f2neg(d));
         u = make_float2(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));    // d > 1 saturates to 1 (u = 0); d < 0 gives u > 1: weight ~ 2^-96
         float2 p;
-        if (TERMS == 5) { p = __ffma2_rn(u, f2bc(k.k5), f2bc(k.k4)); p = __ffma2_rn(u, p, f2bc(k.k3)); }
-        else p = __ffma2_rn(u, f2bc(k.k4), f2bc(k.k3));
-        p = __ffma2_rn(u, p, f2bc(k.k2));
+        if (TERMS == 5) { p = __ffma2_rn(u, f2bc(k.k5), f2bc(k.k4)); p = __ffma2_rn(u, p, f2bc(k.k3)); p = __ffma2_rn(u, p, f2bc(k.k2)); }
+        else if (TERMS == 4) { p = __ffma2_rn(u, f2bc(k.k4), f2bc(k.k3)); p = __ffma2_rn(u, p, f2bc(k.k2)); }
+        else p = __ffma2_rn(u, f2bc(k.k3), f2bc(k.k2));
         p = __ffma2_rn(u, p, f2bc(k.k1));
         e = __ffma2_rn(f2neg(u), p, f2neg(base));
     }
@@ -87,9 +87,9 @@ __device__ __forceinline__ void pk_normal_term(float nx, float ny, float nz, flo
                                                float &u, float &p) {
     const float d = fmaf(nz, qnz, fmaf(ny, qny, nx * qnx));
     u = fmaxf(1.0f - d, 0.0f);
-    if (TERMS == 5) { p = fmaf(u, k.k5, k.k4); p = fmaf(u, p, k.k3); }
-    else p = fmaf(u, k.k4, k.k3);
-    p = fmaf(u, p, k.k2);
+    if (TERMS == 5) { p = fmaf(u, k.k5, k.k4); p = fmaf(u, p, k.k3); p = fmaf(u, p, k.k2); }
+    else if (TERMS == 4) { p = fmaf(u, k.k4, k.k3); p = fmaf(u, p, k.k2); }
+    else p = fmaf(u, k.k3, k.k2);
     p = fmaf(u, p, k.k1);
 }
 
@@ -107,9 +107,9 @@ __device__ __forceinline__ void pk_tap2n(PkAcc &A, const PkCentreN &C, const PkT
     float2 u = __fadd2_rn(f2bc(1.0f), f2neg(d));
     u = make_float2(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));
     float2 p;
-    if (TERMS == 5) { p = __ffma2_rn(u, f2bc(k.k5), f2bc(k.k4)); p = __ffma2_rn(u, p, f2bc(k.k3)); }
-    else p = __ffma2_rn(u, f2bc(k.k4), f2bc(k.k3));
-    p = __ffma2_rn(u, p, f2bc(k.k2));
+    if (TERMS == 5) { p = __ffma2_rn(u, f2bc(k.k5), f2bc(k.k4)); p = __ffma2_rn(u, p, f2bc(k.k3)); p = __ffma2_rn(u, p, f2bc(k.k2)); }
+    else if (TERMS == 4) { p = __ffma2_rn(u, f2bc(k.k4), f2bc(k.k3)); p = __ffma2_rn(u, p, f2bc(k.k2)); }
+    else p = __ffma2_rn(u, f2bc(k.k3), f2bc(k.k2));
     p = __ffma2_rn(u, p, f2bc(k.k1));
     const float2 e = __ffma2_rn(f2neg(u), p, f2neg(base));
     const float2 w = make_float2(fast_exp2(e.x), fast_exp2(e.y));
@@ -142,11 +142,13 @@ __device__ __forceinline__ constexpr float tap_inv_len(int ax, int ay) {
 }
 
 // all 24 taps of the kPkRows outputs of one thread (both pixels of the pair)
-template <int STEP, int TERMS, bool UNIF>
+// PITCH = pixel pairs between consecutive LATTICE rows of the shared-memory planes (the tile's own width for the
+// single-level kernel; the fused two-level kernel passes its staging pitch, doubled for the dilated level)
+template <int STEP, int TERMS, bool UNIF, int PITCH = PackedGeom<STEP>::pairs>
 __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[kPkRows], const PkCentre (&C)[kPkRows], const float4 *sC0, const float4 *sC1,
                                             const float4 *sG0, const float4 *sG1, const float2 *sL, int row0, int pcol,
                                             const PkCoef &k, float un, float pn) {
-    using G = PackedGeom<STEP>;
+    struct G { enum { pairs = PITCH }; };
     if (STEP > 1) {
 #pragma unroll
         for (int dx = -2; dx <= 2; dx++) {
