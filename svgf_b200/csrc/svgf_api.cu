@@ -8,63 +8,16 @@
 #include <new>
 
 #include "../../include/svgf.h"
+#include "svgf_ctx.h"
 #include "svgf_kernels_basic.cuh"
-#include "svgf_kernels_tiled.cuh"
-#include "svgf_kernels_packed.cuh"
-#include "svgf_kernels_stream.cuh"
-#include "svgf_kernels_fused.cuh"
 #include <cstdlib>
 
 using namespace svgf;
-
-struct svgf_ctx {
-    int device = 0, W = 0, H = 0;
-    svgf_storage storage = SVGF_STORE_F16;
-    uint8_t *hist_shadow = nullptr;       // this frame's history lengths until published (D3)
-    Guide guide[2] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // compact guide planes, ping-pong
-    int num_sms = 148;
-    unsigned int *worklist = nullptr;     // indices of short-history pixels queued by the fused temporal pass
-    unsigned int *work_counter = nullptr;
-    const void *guide_key[2] = {nullptr, nullptr};  // motion_depth pointer of the G-buffer each plane was built from
-    int guide_cur = 0;                    // slot of the most recently built guide
-    bool force_fail_next = false;         // set by svgf_reset
-    int last_err = 0;
-    uint64_t launches = 0;
-    // stage profiling (svgf_profile_*): events around temporal / variance / a-trous inside svgf_frame
-    bool profiling = false;
-    static constexpr int kMaxProf = 4096;
-    cudaEvent_t *prof_ev = nullptr;       // 4 events per frame
-    int prof_frames = 0;
-    // device-resident state of the host-buffer path (svgf_frame_host): a 3-slot ring of staged inputs filled on a
-    // copy-in stream, results drained on a copy-out stream, so that the PCIe transfers of frames t+1 and t-1
-    // overlap the kernels of frame t
-    struct HostPath {
-        static constexpr int kRing = 3;
-        void *normal[kRing] = {}, *uv[kRing] = {}, *motion[kRing] = {}, *noisy[kRing] = {};
-        void *render[2] = {nullptr, nullptr}, *moments[2] = {nullptr, nullptr}, *filter[2] = {nullptr, nullptr};
-        uint8_t *history = nullptr;
-        cudaStream_t s_in = nullptr, s_out = nullptr;
-        cudaEvent_t ev_in[kRing] = {}, ev_done[kRing] = {}, ev_out = nullptr;
-        uint64_t frame = 0;                 // frames submitted since the ring was created
-        int ping_pong = 0;
-        bool ready = false;
-    } hp;
-};
 
 namespace {
 
 inline size_t colour_bytes(const svgf_ctx *c) { return (size_t)c->W * c->H * (c->storage == SVGF_STORE_F32 ? 16 : 8); }
 inline size_t moments_bytes(const svgf_ctx *c) { return (size_t)c->W * c->H * (c->storage == SVGF_STORE_F32 ? 8 : 4); }
-
-svgf_status cuda_fail(svgf_ctx *c, cudaError_t e) {
-    if (c) c->last_err = (int)e;
-    return SVGF_CUDA_ERROR;
-}
-#define SVGF_CUDA(c, x)                                    \
-    do {                                                   \
-        cudaError_t e_ = (x);                              \
-        if (e_ != cudaSuccess) return cuda_fail((c), e_);  \
-    } while (0)
 
 svgf_status check_params(const svgf_params *p) {
     if (!p) return SVGF_INVALID_ARG;
@@ -215,118 +168,6 @@ svgf_status launch_variance_sparse(svgf_ctx *c, const svgf_params *p, int guide_
     return SVGF_OK;
 }
 
-template <bool F32, int STEP, int RG, int TERMS>
-svgf_status launch_atrous_tiled(svgf_ctx *c, AtrousTiledArgs a, int guide_slot, const void *in, void *out, void *hist_colour,
-                                cudaStream_t s) {
-    using CT = typename ColourPlane<F32>::texel;
-    using G = TileGeom<F32, STEP, RG>;
-    auto kern = atrous_tiled_kernel<F32, STEP, RG, TERMS>;
-    static int ctas_per_sm[16] = {};   // per device, 0 = not configured yet
-    int &cps = ctas_per_sm[c->device & 15];
-    if (cps == 0) {
-        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
-        int n = 0;
-        SVGF_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, G::threads, G::smem_bytes));
-        if (n < 1) return SVGF_UNSUPPORTED;
-        cps = n;
-    }
-    a.tiles_x = (c->W + kTileW - 1) / kTileW;
-    a.tiles_y = ((c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP)) * STEP;
-    const int n_tiles = a.tiles_x * a.tiles_y;
-    const int grid = n_tiles < c->num_sms * cps ? n_tiles : c->num_sms * cps;
-    kern<<<grid, G::threads, G::smem_bytes, s>>>(a, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in, (CT *)out,
-                                                 (CT *)hist_colour);
-    c->launches++;
-    SVGF_CUDA(c, cudaGetLastError());
-    return SVGF_OK;
-}
-
-template <bool F32, int STEP, int TERMS>
-svgf_status launch_atrous_packed(svgf_ctx *c, AtrousTiledArgs a, int guide_slot, const void *in, void *out, void *hist_colour,
-                                 cudaStream_t s) {
-    using CT = typename ColourPlane<F32>::texel;
-    using G = PackedGeom<STEP>;
-    auto kern = atrous_packed_kernel<F32, STEP, TERMS>;
-    static bool configured[16] = {};
-    if (!configured[c->device & 15]) {
-        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
-        configured[c->device & 15] = true;
-    }
-    const dim3 grid((c->W + kTileW - 1) / kTileW, ((c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP)) * STEP);
-    kern<<<grid, kPkThreads, G::smem_bytes, s>>>(a, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in, (CT *)out,
-                                                 (CT *)hist_colour);
-    c->launches++;
-    SVGF_CUDA(c, cudaGetLastError());
-    return SVGF_OK;
-}
-template <bool F32, int TERMS>
-svgf_status dispatch_atrous_packed(svgf_ctx *c, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out,
-                                   void *hist_colour, cudaStream_t s) {
-    switch (a.level) {
-        case 0: return launch_atrous_packed<F32, 1, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 1: return launch_atrous_packed<F32, 2, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 2: return launch_atrous_packed<F32, 4, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 3: return launch_atrous_packed<F32, 8, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 4: return launch_atrous_packed<F32, 16, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-    }
-    return SVGF_UNSUPPORTED;
-}
-
-template <bool F32, int STEP, int TERMS>
-svgf_status launch_atrous_stream(svgf_ctx *c, const AtrousTiledArgs &t, int guide_slot, const void *in, void *out, void *hist_colour,
-                                 cudaStream_t s) {
-    using CT = typename ColourPlane<F32>::texel;
-    using G = StreamGeom<STEP>;
-    auto kern = atrous_stream_kernel<F32, STEP, TERMS>;
-    static bool configured[16] = {};
-    const size_t smem = G::smem_bytes;
-    if (!configured[c->device & 15]) {
-        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[c->device & 15] = true;
-    }
-    AtrousStreamArgs a;
-    a.t = t;
-    a.n_strips = (c->W + kStripW - 1) / kStripW;
-    a.rows_a = c->H / STEP;
-    a.rows_b = c->H % STEP;
-    // the (strip, phase, row) stream is cut into equal contiguous ranges, one per CTA; two CTAs per SM
-    const long long T = (long long)a.n_strips * c->H;
-    long long grid = 2LL * c->num_sms;
-    if (grid > T / 8) grid = T / 8 > 0 ? T / 8 : 1;
-    kern<<<(unsigned int)grid, kStreamThreads, smem, s>>>(a, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in,
-                                                                    (CT *)out, (CT *)hist_colour);
-    c->launches++;
-    SVGF_CUDA(c, cudaGetLastError());
-    return SVGF_OK;
-}
-template <bool F32, int TERMS>
-svgf_status dispatch_atrous_stream(svgf_ctx *c, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out,
-                                   void *hist_colour, cudaStream_t s) {
-    switch (a.level) {
-        case 0: return launch_atrous_stream<F32, 1, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 1: return launch_atrous_stream<F32, 2, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 2: return launch_atrous_stream<F32, 4, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 3: return launch_atrous_stream<F32, 8, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 4: return launch_atrous_stream<F32, 16, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-    }
-    return SVGF_UNSUPPORTED;
-}
-
-// Row groups per CTA: 2 (256 threads, two CTAs per SM) while the tile fits twice; 4 (512 threads, one CTA per SM,
-// less vertical halo) for the wide-halo levels — chosen so every instantiation fits the 227 KB of shared memory.
-template <bool F32, int TERMS>
-svgf_status dispatch_atrous_tiled(svgf_ctx *c, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out,
-                                  void *hist_colour, cudaStream_t s) {
-    switch (a.level) {
-        case 0: return launch_atrous_tiled<F32, 1, 2, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 1: return launch_atrous_tiled<F32, 2, 2, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 2: return launch_atrous_tiled<F32, 4, 2, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 3: return launch_atrous_tiled<F32, 8, 4, TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-        case 4: return launch_atrous_tiled<F32, 16, (F32 ? 2 : 4), TERMS>(c, a, guide_slot, in, out, hist_colour, s);
-    }
-    return SVGF_UNSUPPORTED;
-}
-
 // Levels 0 and 1 in one launch (svgf_kernels_fused.cuh).  Same preconditions as the packed single-level kernel.
 template <bool F32>
 bool fused01_applicable(const svgf_ctx *c, const svgf_params *p, const void *in, const void *out, const void *hist_colour) {
@@ -334,23 +175,6 @@ bool fused01_applicable(const svgf_ctx *c, const svgf_params *p, const void *in,
     return (p->flags & SVGF_FLAG_FUSE_LEVELS_01) && !(p->flags & (SVGF_FLAG_BASIC_KERNELS | SVGF_FLAG_NO_LEVEL_FUSION)) && nt.series &&
            p->phi_depth > 0.0f && c->W % 2 == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 &&
            (!hist_colour || ((uintptr_t)hist_colour % 16) == 0);
-}
-template <bool F32, int TERMS>
-svgf_status launch_atrous_fused01_t(svgf_ctx *c, const AtrousTiledArgs &t, int guide_slot, const void *in, void *out, void *hist_colour,
-                                    cudaStream_t s) {
-    using CT = typename ColourPlane<F32>::texel;
-    auto kern = atrous_fused01_kernel<F32, TERMS>;
-    static bool configured[16] = {};
-    if (!configured[c->device & 15]) {
-        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedGeom::smem_bytes));
-        configured[c->device & 15] = true;
-    }
-    const dim3 grid((c->W + kFzW - 1) / kFzW, (c->H + kFzH - 1) / kFzH);
-    kern<<<grid, kFzThreads, FusedGeom::smem_bytes, s>>>(t, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in, (CT *)out,
-                                                         (CT *)hist_colour);
-    c->launches++;
-    SVGF_CUDA(c, cudaGetLastError());
-    return SVGF_OK;
 }
 template <bool F32>
 svgf_status launch_atrous_fused01(svgf_ctx *c, const svgf_params *p, int guide_slot, const void *in, void *out, void *hist_colour,
@@ -365,9 +189,9 @@ svgf_status launch_atrous_fused01(svgf_ctx *c, const svgf_params *p, int guide_s
     if (p->phi_normal >= 100.0f) {             // same series selection as the single-level packed dispatch
         const NormalTerm e3 = economised_series3(p->phi_normal);
         t.k1 = e3.k1; t.k2 = e3.k2; t.k3 = e3.k3;
-        return launch_atrous_fused01_t<F32, 3>(c, t, guide_slot, in, out, hist_colour, s);
+        return atrous_fused01(c, F32, 3, t, guide_slot, in, out, hist_colour, s);
     }
-    return launch_atrous_fused01_t<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);
+    return atrous_fused01(c, F32, 5, t, guide_slot, in, out, hist_colour, s);
 }
 
 template <bool F32>
@@ -396,21 +220,20 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
         // (register sliding window; a third of the shared-memory traffic but two consumer warps per sub-partition —
         // measured slower), =bulk the persistent bulk-copy scalar kernel
         if (want_stream && pair_ok)
-            return (p->phi_normal >= 100.0f) ? dispatch_atrous_stream<F32, 4>(c, t, guide_slot, in, out, hist_colour, s)
-                                             : dispatch_atrous_stream<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);
+            return atrous_stream(c, F32, p->phi_normal >= 100.0f ? 4 : 5, t, guide_slot, in, out, hist_colour, s);
         if (!want_bulk && c->W % 2 == 0 && ((uintptr_t)out % 16) == 0 && (!hist_colour || ((uintptr_t)hist_colour % 16) == 0)) {
             if (p->phi_normal >= 100.0f && !(variant && !strcmp(variant, "taylor4"))) {
                 // three-term economised series (svgf_device.cuh, economised_series3): one Horner step fewer per tap,
                 // weight error <= 0.56 / (phiN log2e)^3 <= 1.9e-7 absolute
                 const NormalTerm e3 = economised_series3(p->phi_normal);
                 t.k1 = e3.k1; t.k2 = e3.k2; t.k3 = e3.k3;
-                return dispatch_atrous_packed<F32, 3>(c, t, guide_slot, in, out, hist_colour, s);
+                const int rows = 3;
+                return F32 ? atrous_packed_f32(c, 3, rows, t, guide_slot, in, out, hist_colour, s) : atrous_packed_f16(c, 3, rows, t, guide_slot, in, out, hist_colour, s);
             }
-            return (p->phi_normal >= 100.0f) ? dispatch_atrous_packed<F32, 4>(c, t, guide_slot, in, out, hist_colour, s)
-                                             : dispatch_atrous_packed<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);
+            const int terms = p->phi_normal >= 100.0f ? 4 : 5;
+            return F32 ? atrous_packed_f32(c, terms, 3, t, guide_slot, in, out, hist_colour, s) : atrous_packed_f16(c, terms, 3, t, guide_slot, in, out, hist_colour, s);
         }
-        return (p->phi_normal >= 100.0f) ? dispatch_atrous_tiled<F32, 4>(c, t, guide_slot, in, out, hist_colour, s)
-                                         : dispatch_atrous_tiled<F32, 5>(c, t, guide_slot, in, out, hist_colour, s);
+        return atrous_tiled(c, F32, p->phi_normal >= 100.0f ? 4 : 5, t, guide_slot, in, out, hist_colour, s);
     }
     if (a.nt.series)
         atrous_kernel<F32, true><<<grid_for(c), 256, 0, s>>>(a, c->guide[guide_slot], (const CT *)in, (CT *)out, (CT *)hist_colour);

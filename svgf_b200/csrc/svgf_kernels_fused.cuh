@@ -65,8 +65,8 @@ __device__ __forceinline__ void fused_task(const AtrousTiledArgs &a, float kZ_sc
         C[j].kZ = make_float2(__fdividef(kZ_scale, fmaxf(dz.x, 1e-6f)), __fdividef(kZ_scale, fmaxf(dz.y, 1e-6f)));
     }
     if (__any_sync(__activemask(), any_live)) {
-        if (uniform_n) pk_all_taps<STEP, TERMS, true, PITCH>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, un, pn);
-        else pk_all_taps<STEP, TERMS, false, PITCH>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, 0.f, 0.f);
+        if (uniform_n) pk_all_taps<STEP, TERMS, true, PITCH, kPkRows>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, un, pn);
+        else pk_all_taps<STEP, TERMS, false, PITCH, kPkRows>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, 0.f, 0.f);
     }
 #pragma unroll
     for (int j = 0; j < kPkRows; j++) {

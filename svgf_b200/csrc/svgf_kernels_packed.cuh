@@ -144,8 +144,10 @@ __device__ __forceinline__ constexpr float tap_inv_len(int ax, int ay) {
 // all 24 taps of the kPkRows outputs of one thread (both pixels of the pair)
 // PITCH = pixel pairs between consecutive LATTICE rows of the shared-memory planes (the tile's own width for the
 // single-level kernel; the fused two-level kernel passes its staging pitch, doubled for the dilated level)
-template <int STEP, int TERMS, bool UNIF, int PITCH = PackedGeom<STEP>::pairs>
-__device__ __forceinline__ void pk_all_taps(PkAcc (&A)[kPkRows], const PkCentre (&C)[kPkRows], const float4 *sC0, const float4 *sC1,
+// R = outputs per thread and column: a staged tap row serves up to min(R, 5) of them, so shared-memory traffic per
+// output falls as (R + 4) / R while the per-thread state grows by 24 registers per row.
+template <int STEP, int TERMS, bool UNIF, int PITCH = PackedGeom<STEP>::pairs, int R = kPkRows>
+__device__ __forceinline__ void pk_all_taps(PkAcc (&A)[R], const PkCentre (&C)[R], const float4 *sC0, const float4 *sC1,
                                             const float4 *sG0, const float4 *sG1, const float2 *sL, int row0, int pcol,
                                             const PkCoef &k, float un, float pn) {
     struct G { enum { pairs = PITCH }; };
@@ -153,7 +155,7 @@ __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[kPkRows], const PkCentre 
 #pragma unroll
         for (int dx = -2; dx <= 2; dx++) {
 #pragma unroll
-            for (int t = -2; t < kPkRows + 2; t++) {
+            for (int t = -2; t < R + 2; t++) {
                 const int si = (row0 + t) * G::pairs + pcol + dx * (STEP / 2);
                 const float4 c0 = sC0[si], c1 = sC1[si];
                 float4 g0, g1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -164,7 +166,7 @@ __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[kPkRows], const PkCentre 
                 q.z = make_float2(g0.x, g0.y); q.nx = make_float2(g0.z, g0.w); q.ny = make_float2(g1.x, g1.y); q.nz = make_float2(g1.z, g1.w);
                 q.l = sL[si];
 #pragma unroll
-                for (int j = 0; j < kPkRows; j++) {
+                for (int j = 0; j < R; j++) {
                     const int dy = t - j;
                     if (dy < -2 || dy > 2 || (dx == 0 && dy == 0)) continue;
                     const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
@@ -178,7 +180,7 @@ __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[kPkRows], const PkCentre 
         // taps x-1 = pair(-1).hi and x+1 = pair(0).hi; output 1 (column x+1) taps x = pair(0).lo and x+2 = pair(+1).lo.
         // One pair is live at a time.
 #pragma unroll
-        for (int t = -2; t < kPkRows + 2; t++) {
+        for (int t = -2; t < R + 2; t++) {
 #pragma unroll
             for (int m = -1; m <= 1; m++) {
                 const int si = (row0 + t) * G::pairs + pcol + m;
@@ -191,7 +193,7 @@ __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[kPkRows], const PkCentre 
                 q.z = make_float2(g0.x, g0.y); q.nx = make_float2(g0.z, g0.w); q.ny = make_float2(g1.x, g1.y); q.nz = make_float2(g1.z, g1.w);
                 q.l = sL[si];
 #pragma unroll
-                for (int j = 0; j < kPkRows; j++) {
+                for (int j = 0; j < R; j++) {
                     const int dy = t - j;
                     if (dy < -2 || dy > 2) continue;
                     const int ay = dy < 0 ? -dy : dy;
@@ -212,12 +214,14 @@ __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[kPkRows], const PkCentre 
     }
 }
 
-template <bool F32, int STEP, int TERMS>
-__global__ void __launch_bounds__(kPkThreads, 2)
+template <bool F32, int STEP, int TERMS, int R = kPkRows>
+__global__ void __launch_bounds__(kPkPairs * (PackedGeom<STEP>::tile_rows / R), 2)
 atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, const float *__restrict__ guide_dz,
                      const typename ColourPlane<F32>::texel *__restrict__ in, typename ColourPlane<F32>::texel *__restrict__ out,
                      typename ColourPlane<F32>::texel *__restrict__ hist_colour) {
     using G = PackedGeom<STEP>;
+    constexpr int kThreads = kPkPairs * (G::tile_rows / R);   // R = 3: 256 threads, R = 4: 192
+    static_assert(G::tile_rows % R == 0, "row groups must tile the 12 rows");
     using CT = typename ColourPlane<F32>::texel;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sC0 = reinterpret_cast<float4 *>(smem_raw);        // r0 r1 g0 g1
@@ -239,12 +243,12 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     // NaN never matches.  Texels outside the image are excluded: their weight is 0 through z = +inf either way.
     const float4 nref = __ldg(guide_n + (size_t)min(y0, a.H - 1) * a.W + x0);
     bool same_n = a.uniform_tiles && (nref.y != 0.0f || nref.z != 0.0f || nref.w != 0.0f);
-    constexpr int kIters = (G::npairs + kPkThreads - 1) / kPkThreads;
+    constexpr int kIters = (G::npairs + kThreads - 1) / kThreads;
     CT rc0[kIters], rc1[kIters];
     float4 rg0[kIters], rg1[kIters];
 #pragma unroll
     for (int i = 0; i < kIters; i++) {
-        const int idx = tid + i * kPkThreads;
+        const int idx = tid + i * kThreads;
         const int r = idx / G::pairs, pc = idx - r * G::pairs;
         const int gx = x0 - 2 * STEP + 2 * pc, gy = y0 + (r - 2) * STEP;
         rg0[i] = rg1[i] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);   // null texel: z = +inf, zero normal
@@ -267,7 +271,7 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     }
 #pragma unroll
     for (int i = 0; i < kIters; i++) {
-        const int idx = tid + i * kPkThreads;
+        const int idx = tid + i * kThreads;
         if (idx < G::npairs) {
             const float4 c0 = ColourPlane<F32>::decode(rc0[i]), c1 = ColourPlane<F32>::decode(rc1[i]);
             const float r0 = __saturatef(c0.x), g0 = __saturatef(c0.y), b0 = __saturatef(c0.z), v0 = __saturatef(c0.w);   // :543,:586
@@ -284,21 +288,21 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     const int pcx = tid & (kPkPairs - 1), tg = tid / kPkPairs;
     const int gx = x0 + 2 * pcx;
     const int pcol = pcx + STEP;                      // pair column in shared memory (halo of 2*STEP pixels = STEP pairs)
-    const int row0 = tg * kPkRows + 2;
+    const int row0 = tg * R + 2;
     PkCoef k;
     k.k1 = a.k1; k.k2 = a.k2; k.k3 = a.k3; k.k4 = a.k4; k.k5 = a.k5;
     float un, pn;
     pk_normal_term<TERMS>(nref.y, nref.z, nref.w, nref.y, nref.z, nref.w, k, un, pn);
 
-    PkCentre C[kPkRows];
-    PkAcc A[kPkRows];
-    bool live0[kPkRows], live1[kPkRows];
+    PkCentre C[R];
+    PkAcc A[R];
+    bool live0[R], live1[R];
     bool any_live = false;
 #pragma unroll
-    for (int j = 0; j < kPkRows; j++) {
+    for (int j = 0; j < R; j++) {
         const int si = (row0 + j) * G::pairs + pcol;
         const float4 c0 = sC0[si], c1 = sC1[si], g0 = sG0[si], g1 = sG1[si];
-        const int gy = y0 + (tg * kPkRows + j) * STEP;
+        const int gy = y0 + (tg * R + j) * STEP;
         A[j].S = f2bc(1.0f);                                                       // :567-568
         A[j].r = make_float2(c0.x, c0.y); A[j].g = make_float2(c0.z, c0.w);
         A[j].b = make_float2(c1.x, c1.y); A[j].v = make_float2(c1.z, c1.w);
@@ -316,14 +320,14 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     }
 
     if (__any_sync(0xffffffffu, any_live)) {
-        if (uniform_n) pk_all_taps<STEP, TERMS, true>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, un, pn);
-        else pk_all_taps<STEP, TERMS, false>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, 0.f, 0.f);
+        if (uniform_n) pk_all_taps<STEP, TERMS, true, G::pairs, R>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, un, pn);
+        else pk_all_taps<STEP, TERMS, false, G::pairs, R>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, 0.f, 0.f);
     }
 
     // ---- normalise and store both pixels of the pair (:615-622) ----
 #pragma unroll
-    for (int j = 0; j < kPkRows; j++) {
-        const int gy = y0 + (tg * kPkRows + j) * STEP;
+    for (int j = 0; j < R; j++) {
+        const int gy = y0 + (tg * R + j) * STEP;
         if (gx >= a.W || gy >= a.H) continue;
         const size_t gi = (size_t)gy * a.W + gx;
         const int si = (row0 + j) * G::pairs + pcol;
