@@ -291,7 +291,9 @@ def run_bands(args, rank, world, local):
     dev = torch.device("cuda", local)
     K, Wm = args.steps, args.warmup
     R = K + Wm
-    bf = make_gpu_banded_filter(W, H, rank, world, dev, storage=args.storage, levels=args.levels)
+    L = min(args.band_exchange_from, args.levels)
+    bf = make_gpu_banded_filter(W, H, rank, world, dev, storage=args.storage, levels=args.levels, apron=args.band_apron,
+                                exchange_from_level=L, max_motion_rows=args.band_max_motion, overlap_state=bool(args.band_overlap_state))
     f, band = bf.f, bf.band
     Hl = band.local_height
     cdt = torch.float16 if args.storage == "f16" else torch.float32
@@ -325,6 +327,7 @@ def run_bands(args, rank, world, local):
     e0.record(stream)
     for t in range(Wm, Wm + K):
         step(t)
+    bf.drain()                      # a state exchange posted under the last frame's levels completes inside the timed region
     e1.record(stream)
     barrier(world)
     sampler.stop_flag = True
@@ -336,16 +339,18 @@ def run_bands(args, rank, world, local):
     peak, peak_src = measured_peaks()
     bpp = BYTES_PER_PX[args.storage]
     frame_bytes = (bpp["temporal"] + bpp["variance"] + bpp["atrous_level"] * args.levels + (bpp["atrous_hist"] if args.levels else 0)) * W * H
-    halo_rows = sum(2 << i for i in range(args.levels)) + 3 * 0
-    halo_bytes = 2 * (world - 1) * (halo_rows * W * OUT_BYTES_PER_PX[args.storage] + APRON * W * (OUT_BYTES_PER_PX[args.storage] * 3 // 2 + 1))
+    halo_rows = sum(2 << i for i in range(L, args.levels))
+    halo_bytes = 2 * (world - 1) * (halo_rows * W * OUT_BYTES_PER_PX[args.storage] + bf.state_apron * W * (OUT_BYTES_PER_PX[args.storage] * 3 // 2 + 1))
     value = W * H * K / (ms_max * 1e-3) / 1e9
     return {
         "metric": "svgf_frame_throughput", "value": round(value, 4), "unit": "Gpix/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": round(ms_max / K, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 compute, %s storage" % ("fp16" if args.storage == "f16" else "fp32"), "data": "synthetic",
         "config": {"workload": f"BASELINE configs[3]: {W}x{H} frames in {world} horizontal band(s), temporal + variance + {args.levels} "
-                               f"a-trous levels, per-level halo exchange (NCCL send/recv)", "width": W, "height": H,
-                   "atrous_levels": args.levels, "storage": args.storage, "band_rows": band.y1 - band.y0, "apron_rows": APRON,
+                               f"a-trous levels, halo exchange (NCCL send/recv) before levels >= {L}, state exchange "
+                               f"{'overlapped with levels 1..' if args.band_overlap_state else 'at frame start'}", "width": W, "height": H,
+                   "atrous_levels": args.levels, "storage": args.storage, "band_rows": band.y1 - band.y0, "apron_rows": bf.apron,
+                   "exchange_from_level": L, "overlap_state": bool(args.band_overlap_state), "exchanges_per_frame": 1 + args.levels - L,
                    "halo_bytes_per_frame_all_ranks": int(halo_bytes),
                    "l2": "every step reads a fresh frame"},
         "gpu_launches": int(launches),
@@ -479,6 +484,10 @@ def main():
     ap.add_argument("--cpu-budget-px", type=float, default=1.6e6, help="pixels per frame of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="svgf_params.flags for A/B runs (8 = no uniform-normal tile shortcut)")
+    ap.add_argument("--band-apron", type=int, default=32, help="--mode bands: apron rows on each side of a band")
+    ap.add_argument("--band-exchange-from", type=int, default=0, help="--mode bands: first a-trous level that exchanges its halo (lower levels recompute it in the apron)")
+    ap.add_argument("--band-max-motion", type=int, default=8, help="--mode bands: vertical reach (rows) of the temporal gather covered by the apron")
+    ap.add_argument("--band-overlap-state", type=int, default=0, help="--mode bands: 1 = post the previous-frame state exchange under levels 1..N-1")
     ap.add_argument("--mode", default="streams", choices=["streams", "bands"],
                     help="multi-GPU sharding: independent frame streams per GPU (weak scaling, default) or one frame in "
                          "horizontal bands with per-level halo exchange (strong scaling; BASELINE configs[3], use --workload 8k)")

@@ -14,6 +14,10 @@ vertical neighbours:
     over the whole local image: rows of the apron that lie closer than the stage's reach to the artificial border
     come out wrong, but they are never read for a band row before the next exchange overwrites them.
 
+Two refinements cut the exposed communication (measured in DESIGN.md section 7): levels below `exchange_from_level` skip
+their exchange and let a wider apron absorb their halo (redundant rows instead of a latency-bound send/recv), and the
+previous-frame state exchange can be posted right after level 0 so that it runs under the remaining levels.
+
 The class is backend-agnostic: it drives any object with the SvgfFilter interface (svgf_b200.filter.SvgfFilter on
 a GPU; the CPU checker behind torch CPU views in the world_size-2 gloo test) through the three
 callables below, so the partition / exchange logic is identical in both.
@@ -53,18 +57,30 @@ def band_of(H, world, rank, apron=APRON):
     return Band(rank, world, H, y0, y1, max(0, y0 - apron), min(H, y1 + apron))
 
 
-def check_partition(H, world, levels, apron=APRON):
-    if levels > MAX_LEVELS or 2 * (1 << max(levels - 1, 0)) > apron:
-        raise ValueError(f"{levels} a-trous levels need a {2 << (levels - 1)}-row apron (> {apron})")
+def required_apron(levels, exchange_from_level=0, max_motion_rows=0):
+    """Apron rows a band needs when a-trous levels < exchange_from_level run WITHOUT a halo exchange (their halo is
+    computed redundantly in the apron) and the others exchange 2 * 2^level rows first.  A stage's output is right only
+    `reach` rows further in from the artificial border than its input was: temporal `max_motion_rows` (the gather at the
+    motion-vector target), variance 3 (7x7 window), level i 2 * 2^i."""
+    L = min(max(exchange_from_level, 0), levels)
+    redundant = (3 + max_motion_rows + sum(2 << i for i in range(L))) if L > 0 else 0
+    exchanged = max([2 << i for i in range(L, levels)], default=0)
+    return max(redundant, exchanged)
+
+
+def check_partition(H, world, levels, apron=APRON, exchange_from_level=0, max_motion_rows=0):
+    need = required_apron(levels, exchange_from_level, max_motion_rows)
+    if need > apron:
+        raise ValueError(f"{levels} a-trous levels (halo exchange from level {exchange_from_level}) need a {need}-row apron (> {apron})")
     if world > 1 and H // world < apron:
         raise ValueError(f"bands of {H // world} rows are shorter than the {apron}-row halo: use fewer ranks")
 
 
-def exchange_rows(band, planes, rows, group=None):
-    """Refresh `rows` apron rows on each side of the band in every tensor of `planes` (local images, dim 0 = rows)
-    with the neighbours' band rows.  One batched send/recv per call; a no-op on one rank."""
+def post_exchange(band, planes, rows, group=None):
+    """Start the exchange of `rows` apron rows on each side of the band for every tensor of `planes` and return the
+    pending work handles ([] on one rank); finish_exchange() completes it.  One batched send/recv."""
     if band.world == 1 or rows <= 0:
-        return
+        return []
     ops, keep = [], []
     up, down = band.rank - 1, band.rank + 1
     for t in planes:
@@ -78,8 +94,18 @@ def exchange_rows(band, planes, rows, group=None):
             recv = t[band.loc(band.y1):band.loc(band.y1 + rows)]
             ops += [dist.P2POp(dist.isend, send, down, group), dist.P2POp(dist.irecv, recv, down, group)]
             keep += [send, recv]
-    for w in dist.batch_isend_irecv(ops):
+    return [(w, keep) for w in dist.batch_isend_irecv(ops)]
+
+
+def finish_exchange(pending):
+    for w, _ in pending:
         w.wait()
+
+
+def exchange_rows(band, planes, rows, group=None):
+    """Refresh `rows` apron rows on each side of the band in every tensor of `planes` (local images, dim 0 = rows)
+    with the neighbours' band rows.  One batched send/recv per call; a no-op on one rank."""
+    finish_exchange(post_exchange(band, planes, rows, group))
 
 
 class BandedFilter:
@@ -92,30 +118,59 @@ class BandedFilter:
               'as_tensor'(buffer) -> torch tensor view of a backend buffer (identity for SvgfFilter).
     """
 
-    def __init__(self, backend, band, ops, levels=5, state_apron=APRON, group=None):
-        check_partition(band.H, band.world, levels)
+    def __init__(self, backend, band, ops, levels=5, state_apron=None, group=None, exchange_from_level=0, max_motion_rows=0,
+                 overlap_state=False):
+        """exchange_from_level : a-trous levels below it skip the halo exchange and rely on the apron instead (0 = exchange
+                              before every level; `levels` = no per-level exchange at all, one state exchange per frame);
+        max_motion_rows     : vertical reach of the temporal gather the apron has to cover in that mode;
+        overlap_state       : post the previous-frame state exchange of frame t+1 right after level 0 of frame t (the
+                              three planes are final by then) so that it runs under levels 1..N-1."""
+        self.apron = max(band.y0 - band.ly0, band.ly1 - band.y1) if band.world > 1 else APRON
+        check_partition(band.H, band.world, levels, self.apron if band.world > 1 else 1 << 30, exchange_from_level, max_motion_rows)
         self.f, self.band, self.ops, self.levels, self.group = backend, band, ops, levels, group
-        self.state_apron = min(state_apron, APRON)
+        self.exchange_from_level = exchange_from_level
+        self.state_apron = self.apron if state_apron is None else min(state_apron, self.apron)
+        self.overlap_state = overlap_state
+        self._pending_state = None
         self.frame = 0
 
     def _t(self, buf):
         return self.ops["as_tensor"](buf)
 
+    def _state_planes(self, idx):
+        f = self.f
+        return [self._t(f.RenderBuffer[idx]), self._t(f.MomentsBuffer[idx]), self._t(f.HistoryLengthBuffer)]
+
     def Filter(self):
         f, b = self.f, self.band
         P, Q = f.PingPongInx, 1 - f.PingPongInx
-        if self.frame > 0:      # previous-frame state in the aprons (the reset frame has none)
-            exchange_rows(b, [self._t(f.RenderBuffer[Q]), self._t(f.MomentsBuffer[Q]), self._t(f.HistoryLengthBuffer)],
-                          self.state_apron, self.group)
+        if self._pending_state is not None:     # posted under the previous frame's levels 1..N-1
+            finish_exchange(self._pending_state)
+            self._pending_state = None
+        elif self.frame > 0:                    # previous-frame state in the aprons (the reset frame has none)
+            exchange_rows(b, self._state_planes(Q), self.state_apron, self.group)
         src = self.ops["temporal_variance"](f)                    # -> FilterBuffer[k] holding the variance pass's output
         k = 0 if src is f.FilterBuffer[0] else 1
         for level in range(self.levels):
-            exchange_rows(b, [self._t(f.FilterBuffer[k])], 2 << level, self.group)
+            if level >= self.exchange_from_level:
+                exchange_rows(b, [self._t(f.FilterBuffer[k])], 2 << level, self.group)
             self.ops["atrous_level"](f, level, f.FilterBuffer[k], f.FilterBuffer[1 - k])
             k = 1 - k
+            if level == 0 and self.overlap_state:
+                # colour history (written by level 0), moments and history lengths of THIS frame are final: they are the
+                # next frame's previous-frame state
+                self._pending_state = post_exchange(b, self._state_planes(P), self.state_apron, self.group)
+        if self.levels == 0 and self.overlap_state:
+            self._pending_state = post_exchange(b, self._state_planes(P), self.state_apron, self.group)
         self.result_index = k
         self.frame += 1
         return f.FilterBuffer[k]
+
+    def drain(self):
+        """Complete a posted state exchange (call before reading state planes from outside or tearing down)."""
+        if self._pending_state is not None:
+            finish_exchange(self._pending_state)
+            self._pending_state = None
 
     def result_band(self):
         """The owned rows of the final result (a view into the local image)."""
@@ -154,9 +209,11 @@ def _gpu_atrous_level(f, level, src, dst):
 GPU_OPS = {"temporal_variance": _gpu_temporal_variance, "atrous_level": _gpu_atrous_level, "as_tensor": lambda t: t}
 
 
-def make_gpu_banded_filter(W, H, rank, world, device, storage="f16", levels=5, group=None):
+def make_gpu_banded_filter(W, H, rank, world, device, storage="f16", levels=5, group=None, apron=APRON, exchange_from_level=0,
+                           max_motion_rows=0, overlap_state=False):
     from .filter import SvgfFilter
-    band = band_of(H, world, rank)
+    band = band_of(H, world, rank, apron)
     f = SvgfFilter(W, band.local_height, device=device, storage=storage)
     f.SpatialFilterSteps = levels
-    return BandedFilter(f, band, GPU_OPS, levels=levels, group=group)
+    return BandedFilter(f, band, GPU_OPS, levels=levels, group=group, exchange_from_level=exchange_from_level,
+                        max_motion_rows=max_motion_rows, overlap_state=overlap_state)

@@ -16,9 +16,16 @@ import torch.multiprocessing as mp
 
 from oracle_lib import OracleFilter, oracle
 from svgf_b200 import synth
-from svgf_b200.bands import APRON, BandedFilter, band_of, check_partition
+from svgf_b200.bands import APRON, BandedFilter, band_of, check_partition, required_apron
 
 W, H, FRAMES, LEVELS = 64, 96, 3, 5
+# (image height, apron rows, first level that exchanges its halo, state exchange posted under levels 1..N-1)
+MODES = {
+    "exchange_every_level": (96, APRON, 0, False),
+    "levels_0_2_redundant_state_overlapped": (96, APRON, 3, True),
+    "no_level_exchange_state_overlapped": (160, 76, 5, True),
+}
+MAX_MOTION_ROWS = 8
 
 
 def test_band_geometry():
@@ -34,6 +41,11 @@ def test_band_geometry():
         check_partition(96, 8, 5)                             # 12-row bands cannot feed a 32-row halo
     with pytest.raises(ValueError):
         check_partition(4320, 2, 6)                           # a sixth level needs a 64-row apron
+    # halo of the levels that do not exchange + variance window + motion reach, or the widest exchanged halo
+    assert required_apron(5, 0) == 32 and required_apron(5, 3, 8) == 32 and required_apron(5, 5, 8) == 3 + 8 + 62
+    with pytest.raises(ValueError):
+        check_partition(4320, 8, 5, apron=32, exchange_from_level=5, max_motion_rows=8)
+    check_partition(4320, 8, 5, apron=76, exchange_from_level=5, max_motion_rows=8)
 
 
 # ---- oracle backend for BandedFilter -------------------------------------------------------------------------------
@@ -57,17 +69,17 @@ def _as_tensor(a):
 ORACLE_OPS = {"temporal_variance": _o_temporal_variance, "atrous_level": _o_atrous_level, "as_tensor": _as_tensor}
 
 
-def _frames():
+def _frames(H=H):
     # vertical motion of ~2.5 px/frame so that reprojection crosses the band boundary
     return [synth.frame_host(W, H, t, vert_px=2.5) for t in range(FRAMES)]
 
 
-def _full_oracle():
+def _full_oracle(H=H):
     o = OracleFilter(W, H, storage="f16")
     o.params.atrous_iterations = LEVELS
     o.Reset()
     outs = []
-    for planes in _frames():
+    for planes in _frames(H):
         o.set_inputs(planes)
         o.Filter()
         outs.append((o.FilterBuffer[0].copy(), o.HistoryLengthBuffer.copy(), o.RenderBuffer[o.PingPongInx].copy()))
@@ -75,22 +87,25 @@ def _full_oracle():
     return outs
 
 
-def _worker(rank, world, port, tmp):
+def _worker(rank, world, port, tmp, mode="exchange_every_level"):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        band = band_of(H, world, rank)
+        Hm, apron, from_level, overlap = MODES[mode]
+        band = band_of(Hm, world, rank, apron)
         o = OracleFilter(W, band.local_height, storage="f16")
         o.params.atrous_iterations = LEVELS
         o.Reset()
-        bf = BandedFilter(o, band, ORACLE_OPS, levels=LEVELS)
-        for t, planes in enumerate(_frames()):
+        bf = BandedFilter(o, band, ORACLE_OPS, levels=LEVELS, exchange_from_level=from_level, max_motion_rows=MAX_MOTION_ROWS,
+                          overlap_state=overlap)
+        for t, planes in enumerate(_frames(Hm)):
             o.set_inputs({k: v[band.ly0:band.ly1] for k, v in planes.items()})
             res = bf.Filter()
             P = o.PingPongInx
             sl = slice(band.loc(band.y0), band.loc(band.y1))
             np.savez(os.path.join(tmp, f"r{rank}_f{t}.npz"), result=res[sl], history=o.HistoryLengthBuffer[sl], colour=o.RenderBuffer[P][sl])
             bf.EndFrame()
+        bf.drain()
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -102,10 +117,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("world", [2])
-def test_bands_with_halo_exchange_equal_the_whole_frame_gloo(world, tmp_path):
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    want = _full_oracle()
+def test_bands_with_halo_exchange_equal_the_whole_frame_gloo(world, mode, tmp_path):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True)
+    want = _full_oracle(MODES[mode][0])
     for t in range(FRAMES):
         parts = [np.load(tmp_path / f"r{r}_f{t}.npz") for r in range(world)]
         for key, idx in (("result", 0), ("history", 1), ("colour", 2)):
