@@ -285,20 +285,27 @@ def run_bands(args, rank, world, local):
     per-level halo rows exchanged between neighbouring ranks (NCCL send/recv over NVLink); strong scaling."""
     import torch
     from svgf_b200 import synth
-    from svgf_b200.bands import APRON, make_gpu_banded_filter
+    from svgf_b200.bands import balanced_bounds, make_gpu_banded_filter
     from svgf_b200.filter import GBuffer
     W, H = WORKLOADS[args.workload]
     dev = torch.device("cuda", local)
     K, Wm = args.steps, args.warmup
     R = K + Wm
     L = min(args.band_exchange_from, args.levels)
-    bf = make_gpu_banded_filter(W, H, rank, world, dev, storage=args.storage, levels=args.levels, apron=args.band_apron,
-                                exchange_from_level=L, max_motion_rows=args.band_max_motion, overlap_state=bool(args.band_overlap_state))
-    f, band = bf.f, bf.band
-    Hl = band.local_height
     cdt = torch.float16 if args.storage == "f16" else torch.float32
     # every rank generates the full frames procedurally on its own GPU and keeps only its local rows (band + aprons)
     full_g, full_c = GBuffer(W, H, dev), torch.empty(H, W, 4, dtype=cdt, device=dev)
+    bounds = None
+    if args.band_balance and world > 1:
+        # equal estimated work per band: background pixels (linear depth 0) are passed through by the a-trous levels
+        synth.frame_device(full_g, full_c, 0, seed=0)
+        live = (full_g.motion[..., 2] != 0).float().mean(dim=1).cpu().numpy()
+        bounds = balanced_bounds(live + args.band_bg_cost * (1.0 - live), world, min_rows=args.band_apron)
+    bf = make_gpu_banded_filter(W, H, rank, world, dev, storage=args.storage, levels=args.levels, apron=args.band_apron,
+                                exchange_from_level=L, max_motion_rows=args.band_max_motion, overlap_state=bool(args.band_overlap_state),
+                                bounds=bounds)
+    f, band = bf.f, bf.band
+    Hl = band.local_height
     ring_g = [GBuffer(W, Hl, dev) for _ in range(R)]
     ring_c = [torch.empty(Hl, W, 4, dtype=cdt, device=dev) for _ in range(R)]
     for t in range(R):
@@ -350,7 +357,7 @@ def run_bands(args, rank, world, local):
                                f"a-trous levels, halo exchange (NCCL send/recv) before levels >= {L}, state exchange "
                                f"{'overlapped with levels 1..' if args.band_overlap_state else 'at frame start'}", "width": W, "height": H,
                    "atrous_levels": args.levels, "storage": args.storage, "band_rows": band.y1 - band.y0, "apron_rows": bf.apron,
-                   "exchange_from_level": L, "overlap_state": bool(args.band_overlap_state), "exchanges_per_frame": 1 + args.levels - L,
+                   "band_bounds": bounds, "exchange_from_level": L, "overlap_state": bool(args.band_overlap_state), "exchanges_per_frame": 1 + args.levels - L,
                    "halo_bytes_per_frame_all_ranks": int(halo_bytes),
                    "l2": "every step reads a fresh frame"},
         "gpu_launches": int(launches),
@@ -484,6 +491,8 @@ def main():
     ap.add_argument("--cpu-budget-px", type=float, default=1.6e6, help="pixels per frame of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0, help="svgf_params.flags for A/B runs (8 = no uniform-normal tile shortcut)")
+    ap.add_argument("--band-balance", type=int, default=1, help="--mode bands: 1 = band heights balanced by estimated work (background rows are cheap), 0 = equal heights")
+    ap.add_argument("--band-bg-cost", type=float, default=0.2, help="--mode bands: cost of a background pixel relative to a filtered one")
     ap.add_argument("--band-apron", type=int, default=32, help="--mode bands: apron rows on each side of a band")
     ap.add_argument("--band-exchange-from", type=int, default=0, help="--mode bands: first a-trous level that exchanges its halo (lower levels recompute it in the apron)")
     ap.add_argument("--band-max-motion", type=int, default=8, help="--mode bands: vertical reach (rows) of the temporal gather covered by the apron")

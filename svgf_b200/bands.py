@@ -50,11 +50,41 @@ class Band:
         return gy - self.ly0
 
 
-def band_of(H, world, rank, apron=APRON):
-    base, rem = divmod(H, world)
-    y0 = rank * base + min(rank, rem)
-    y1 = y0 + base + (1 if rank < rem else 0)
+def band_of(H, world, rank, apron=APRON, bounds=None):
+    """Band of `rank`: equal row counts, or the rows [bounds[rank], bounds[rank + 1]) of balanced_bounds()."""
+    if bounds is not None:
+        if len(bounds) != world + 1 or bounds[0] != 0 or bounds[-1] != H or any(b1 <= b0 for b0, b1 in zip(bounds, bounds[1:])):
+            raise ValueError("bounds must be world + 1 increasing row indices from 0 to H")
+        y0, y1 = int(bounds[rank]), int(bounds[rank + 1])
+    else:
+        base, rem = divmod(H, world)
+        y0 = rank * base + min(rank, rem)
+        y1 = y0 + base + (1 if rank < rem else 0)
     return Band(rank, world, H, y0, y1, max(0, y0 - apron), min(H, y1 + apron))
+
+
+def balanced_bounds(row_cost, world, min_rows=APRON):
+    """Band boundaries with (nearly) equal summed `row_cost` per band instead of equal row counts.
+
+    The a-trous levels skip background pixels (reference src/Filter.cuh:554-558) and take a cheaper path on uniform
+    tiles, so rows cost very different amounts; with equal-height bands the slowest rank sets the frame time.  row_cost
+    is any per-row estimate every rank can compute identically (bench.py: fraction of non-background pixels of the
+    first frame, background weighted 0.2).  Every band keeps at least `min_rows` rows (it must be able to feed its
+    neighbours' aprons)."""
+    import numpy as np
+    c = np.maximum(np.asarray(row_cost, dtype=np.float64), 0.0) + 1e-9
+    H = c.shape[0]
+    if world * min_rows > H:
+        raise ValueError(f"{world} bands of at least {min_rows} rows do not fit {H} rows")
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    bounds = [0]
+    for k in range(1, world):
+        y = int(np.argmin(np.abs(cum - cum[-1] * k / world)))      # boundary whose cumulative cost is nearest the k-th share
+        y = max(y, bounds[-1] + min_rows)              # keep the band above tall enough ...
+        y = min(y, H - (world - k) * min_rows)         # ... and leave room for the ones below
+        bounds.append(y)
+    bounds.append(H)
+    return bounds
 
 
 def required_apron(levels, exchange_from_level=0, max_motion_rows=0):
@@ -74,6 +104,11 @@ def check_partition(H, world, levels, apron=APRON, exchange_from_level=0, max_mo
         raise ValueError(f"{levels} a-trous levels (halo exchange from level {exchange_from_level}) need a {need}-row apron (> {apron})")
     if world > 1 and H // world < apron:
         raise ValueError(f"bands of {H // world} rows are shorter than the {apron}-row halo: use fewer ranks")
+
+
+def check_band(band, apron):
+    if band.world > 1 and band.y1 - band.y0 < apron:
+        raise ValueError(f"band of {band.y1 - band.y0} rows is shorter than the {apron}-row halo")
 
 
 def post_exchange(band, planes, rows, group=None):
@@ -127,6 +162,7 @@ class BandedFilter:
                               three planes are final by then) so that it runs under levels 1..N-1."""
         self.apron = max(band.y0 - band.ly0, band.ly1 - band.y1) if band.world > 1 else APRON
         check_partition(band.H, band.world, levels, self.apron if band.world > 1 else 1 << 30, exchange_from_level, max_motion_rows)
+        check_band(band, self.apron)
         self.f, self.band, self.ops, self.levels, self.group = backend, band, ops, levels, group
         self.exchange_from_level = exchange_from_level
         self.state_apron = self.apron if state_apron is None else min(state_apron, self.apron)
@@ -210,9 +246,9 @@ GPU_OPS = {"temporal_variance": _gpu_temporal_variance, "atrous_level": _gpu_atr
 
 
 def make_gpu_banded_filter(W, H, rank, world, device, storage="f16", levels=5, group=None, apron=APRON, exchange_from_level=0,
-                           max_motion_rows=0, overlap_state=False):
+                           max_motion_rows=0, overlap_state=False, bounds=None):
     from .filter import SvgfFilter
-    band = band_of(H, world, rank, apron)
+    band = band_of(H, world, rank, apron, bounds)
     f = SvgfFilter(W, band.local_height, device=device, storage=storage)
     f.SpatialFilterSteps = levels
     return BandedFilter(f, band, GPU_OPS, levels=levels, group=group, exchange_from_level=exchange_from_level,

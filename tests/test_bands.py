@@ -16,7 +16,7 @@ import torch.multiprocessing as mp
 
 from oracle_lib import OracleFilter, oracle
 from svgf_b200 import synth
-from svgf_b200.bands import APRON, BandedFilter, band_of, check_partition, required_apron
+from svgf_b200.bands import APRON, BandedFilter, balanced_bounds, band_of, check_partition, required_apron
 
 W, H, FRAMES, LEVELS = 64, 96, 3, 5
 # (image height, apron rows, first level that exchanges its halo, state exchange posted under levels 1..N-1)
@@ -24,7 +24,9 @@ MODES = {
     "exchange_every_level": (96, APRON, 0, False),
     "levels_0_2_redundant_state_overlapped": (96, APRON, 3, True),
     "no_level_exchange_state_overlapped": (160, 76, 5, True),
+    "unequal_bands": (96, APRON, 0, False),
 }
+BOUNDS = {"unequal_bands": [0, 60, 96]}
 MAX_MOTION_ROWS = 8
 
 
@@ -46,6 +48,23 @@ def test_band_geometry():
     with pytest.raises(ValueError):
         check_partition(4320, 8, 5, apron=32, exchange_from_level=5, max_motion_rows=8)
     check_partition(4320, 8, 5, apron=76, exchange_from_level=5, max_motion_rows=8)
+
+
+def test_balanced_bounds():
+    cost = np.concatenate([np.full(750, 0.2), np.ones(4320 - 750)])          # cheap background rows on top
+    for world in (2, 4, 8):
+        b = balanced_bounds(cost, world, min_rows=80)
+        assert b[0] == 0 and b[-1] == 4320 and len(b) == world + 1
+        work = [cost[b[k]:b[k + 1]].sum() for k in range(world)]
+        assert max(work) / (cost.sum() / world) < 1.02                         # within 2 % of a perfect split
+        assert min(b1 - b0 for b0, b1 in zip(b, b[1:])) >= 80
+        assert b[1] > 4320 // world                                            # the top band is taller than an equal split
+    assert balanced_bounds(np.ones(96), 2) == [0, 48, 96]
+    assert balanced_bounds(np.r_[np.zeros(90), np.ones(6)], 2, min_rows=32) == [0, 64, 96]   # min_rows wins over balance
+    with pytest.raises(ValueError):
+        balanced_bounds(np.ones(96), 4, min_rows=32)
+    with pytest.raises(ValueError):
+        band_of(96, 2, 0, bounds=[0, 96])
 
 
 # ---- oracle backend for BandedFilter -------------------------------------------------------------------------------
@@ -92,7 +111,7 @@ def _worker(rank, world, port, tmp, mode="exchange_every_level"):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         Hm, apron, from_level, overlap = MODES[mode]
-        band = band_of(Hm, world, rank, apron)
+        band = band_of(Hm, world, rank, apron, BOUNDS.get(mode))
         o = OracleFilter(W, band.local_height, storage="f16")
         o.params.atrous_iterations = LEVELS
         o.Reset()
