@@ -484,6 +484,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k", choices=sorted(WORKLOADS))
+    ap.add_argument("--size", default=None, help="WxH override of --workload (diagnostics; e.g. 7680x2240 = one band of an 8K frame)")
     ap.add_argument("--storage", default="f16", choices=["f16", "f32"])
     ap.add_argument("--levels", type=int, default=5)
     ap.add_argument("--ring", type=int, default=200, help="max distinct frames kept resident in HBM")
@@ -494,13 +495,17 @@ def main():
     ap.add_argument("--band-balance", type=int, default=1, help="--mode bands: 1 = band heights balanced by estimated work (background rows are cheap), 0 = equal heights")
     ap.add_argument("--band-bg-cost", type=float, default=0.2, help="--mode bands: cost of a background pixel relative to a filtered one")
     ap.add_argument("--band-apron", type=int, default=32, help="--mode bands: apron rows on each side of a band")
-    ap.add_argument("--band-exchange-from", type=int, default=0, help="--mode bands: first a-trous level that exchanges its halo (lower levels recompute it in the apron)")
+    ap.add_argument("--band-exchange-from", type=int, default=3, help="--mode bands: first a-trous level that exchanges its halo (lower levels recompute it in the apron)")
     ap.add_argument("--band-max-motion", type=int, default=8, help="--mode bands: vertical reach (rows) of the temporal gather covered by the apron")
-    ap.add_argument("--band-overlap-state", type=int, default=0, help="--mode bands: 1 = post the previous-frame state exchange under levels 1..N-1")
+    ap.add_argument("--band-overlap-state", type=int, default=1, help="--mode bands: 1 = post the previous-frame state exchange under levels 1..N-1")
     ap.add_argument("--mode", default="streams", choices=["streams", "bands"],
                     help="multi-GPU sharding: independent frame streams per GPU (weak scaling, default) or one frame in "
                          "horizontal bands with per-level halo exchange (strong scaling; BASELINE configs[3], use --workload 8k)")
     args = ap.parse_args()
+    if args.size:
+        w_, h_ = (int(v) for v in args.size.lower().split("x"))
+        WORKLOADS[args.size] = (w_, h_)
+        args.workload = args.size
     if args.warmup < 3:
         args.warmup = 3
     if args.workload == "8k":
