@@ -58,8 +58,12 @@ typedef enum svgf_mesh_id_mode { SVGF_MESH_ID_INTENDED = 0, SVGF_MESH_ID_REFEREN
 /* History fetch.  NEAREST_TRUNC is what the reference does (src/Filter.cuh:231-232). */
 typedef enum svgf_reproj_mode { SVGF_REPROJ_NEAREST_TRUNC = 0 } svgf_reproj_mode;
 
-/* Variance pre-filter of the a-trous levels.  NONE is what the reference does (src/Filter.cuh:547,562). */
-typedef enum svgf_variance_prefilter { SVGF_VARIANCE_PREFILTER_NONE = 0 } svgf_variance_prefilter;
+/* Variance pre-filter of the a-trous levels.  NONE is what the reference does (src/Filter.cuh:547,562: the centre
+ * texel's own variance scales the luminance edge-stopping term).  GAUSS3 is the SVGF paper's form, which the reference
+ * leaves out: that variance is first blurred with the 3x3 kernel (1 2 1; 2 4 2; 1 2 1) / 16 over the level's INPUT
+ * plane at +-1 pixel (not dilated), separably - rows y-1, y, y+1 combined first, then columns - with coordinates
+ * clamped to the image; everything else is unchanged. */
+typedef enum svgf_variance_prefilter { SVGF_VARIANCE_PREFILTER_NONE = 0, SVGF_VARIANCE_PREFILTER_GAUSS3 = 1 } svgf_variance_prefilter;
 
 /* svgf_params.flags */
 #define SVGF_FLAG_NONE 0u

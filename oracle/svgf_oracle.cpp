@@ -182,7 +182,8 @@ int check_common(const svgf_params *p, int W, int H, int storage) {
     if (storage != SVGF_STORE_F16 && storage != SVGF_STORE_F32) return SVGF_INVALID_ARG;
     if (p->history_cap < 1 || p->history_cap > 255) return SVGF_INVALID_ARG;  // D9
     if (p->atrous_iterations < 0 || p->atrous_iterations > 10) return SVGF_INVALID_ARG;
-    if (p->reproj_mode != SVGF_REPROJ_NEAREST_TRUNC || p->variance_prefilter != SVGF_VARIANCE_PREFILTER_NONE)
+    if (p->reproj_mode != SVGF_REPROJ_NEAREST_TRUNC) return SVGF_UNSUPPORTED;
+    if (p->variance_prefilter != SVGF_VARIANCE_PREFILTER_NONE && p->variance_prefilter != SVGF_VARIANCE_PREFILTER_GAUSS3)
         return SVGF_UNSUPPORTED;
     return SVGF_OK;
 }
@@ -294,6 +295,21 @@ void variance(const svgf_params &P, int W, int H, const GBuf &G, const void *in,
     }
 }
 
+// SVGF_VARIANCE_PREFILTER_GAUSS3 (include/svgf.h; not in the reference): the clamped variance of the level's input
+// blurred with (1 2 1; 2 4 2; 1 2 1) / 16, rows first, coordinates clamped to the image.
+template <bool F32>
+float variance_gauss3(const void *in, int W, int H, int x, int y) {
+    float col[3];
+    for (int dx = -1; dx <= 1; dx++) {
+        const int px = x + dx < 0 ? 0 : (x + dx >= W ? W - 1 : x + dx);
+        const int ym = y > 0 ? y - 1 : 0, yp = y < H - 1 ? y + 1 : H - 1;
+        const float a = Colour<F32>::ld01(in, (size_t)ym * W + px).w, b = Colour<F32>::ld01(in, (size_t)y * W + px).w,
+                    c = Colour<F32>::ld01(in, (size_t)yp * W + px).w;
+        col[dx + 1] = (0.25f * a + 0.5f * b) + 0.25f * c;
+    }
+    return (0.25f * col[0] + 0.5f * col[1]) + 0.25f * col[2];
+}
+
 // ---- A.4 a-trous level: src/Filter.cuh:527-624 -----------------------------------------------------------
 template <bool F32>
 void atrous(const svgf_params &P, int W, int H, const GBuf &G, const void *in, void *out, void *hist_colour, int level) {
@@ -305,7 +321,8 @@ void atrous(const svgf_params &P, int W, int H, const GBuf &G, const void *in, v
             const size_t i = (size_t)y * W + x;
             const V4 c = Colour<F32>::ld01(in, i);                                   // :543
             const float lc = lum(c.x, c.y, c.z);                                     // :544
-            const float var = c.w;                                                   // :547
+            const float var = (P.variance_prefilter == SVGF_VARIANCE_PREFILTER_GAUSS3) ? variance_gauss3<F32>(in, W, H, x, y)
+                                                                                       : c.w;  // :547
             const V2 zc = G.depth(x, y);                                             // :552
             if (zc.x == 1e30f) {                                                     // :554-558
                 Colour<F32>::store_raw(out, i, c);

@@ -29,7 +29,8 @@ svgf_status check_params(const svgf_params *p) {
         return SVGF_INVALID_ARG;
     if (p->mesh_id_mode != SVGF_MESH_ID_INTENDED && p->mesh_id_mode != SVGF_MESH_ID_REFERENCE_VACUOUS) return SVGF_INVALID_ARG;
     if (p->reproj_mode != SVGF_REPROJ_NEAREST_TRUNC) return SVGF_UNSUPPORTED;
-    if (p->variance_prefilter != SVGF_VARIANCE_PREFILTER_NONE) return SVGF_UNSUPPORTED;
+    if (p->variance_prefilter != SVGF_VARIANCE_PREFILTER_NONE && p->variance_prefilter != SVGF_VARIANCE_PREFILTER_GAUSS3)
+        return SVGF_UNSUPPORTED;
     return SVGF_OK;
 }
 
@@ -130,6 +131,7 @@ SpatialArgs spatial_args(const svgf_ctx *c, const svgf_params *p, int level) {
     a.phi_colour = p->phi_colour; a.phi_depth = p->phi_depth;
     a.nt = make_normal_term(p->phi_normal);
     a.step = 1 << level; a.level = level;
+    a.var_blur = nullptr;
     return a;
 }
 
@@ -173,6 +175,7 @@ template <bool F32>
 bool fused01_applicable(const svgf_ctx *c, const svgf_params *p, const void *in, const void *out, const void *hist_colour) {
     const NormalTerm nt = make_normal_term(p->phi_normal);
     return (p->flags & SVGF_FLAG_FUSE_LEVELS_01) && !(p->flags & (SVGF_FLAG_BASIC_KERNELS | SVGF_FLAG_NO_LEVEL_FUSION)) && nt.series &&
+           p->variance_prefilter == SVGF_VARIANCE_PREFILTER_NONE &&
            p->phi_depth > 0.0f && c->W % 2 == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 &&
            (!hist_colour || ((uintptr_t)hist_colour % 16) == 0);
 }
@@ -183,6 +186,7 @@ svgf_status launch_atrous_fused01(svgf_ctx *c, const svgf_params *p, int guide_s
     AtrousTiledArgs t;
     t.W = c->W; t.H = c->H; t.level = 0; t.tiles_x = t.tiles_y = 0;
     t.uniform_tiles = (p->flags & SVGF_FLAG_NO_UNIFORM_TILES) ? 0 : 1;
+    t.var_blur = nullptr;
     t.kL_scale = kLog2e / p->phi_colour;
     t.kZ_scale = kLog2e / p->phi_depth;        // level 0; the kernel halves it for level 1
     t.k1 = a.nt.k1; t.k2 = a.nt.k2; t.k3 = a.nt.k3; t.k4 = a.nt.k4; t.k5 = a.nt.k5;
@@ -198,7 +202,17 @@ template <bool F32>
 svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slot, const void *in, void *out,
                                 void *hist_colour, int level, cudaStream_t s) {
     using CT = typename ColourPlane<F32>::texel;
-    const SpatialArgs a = spatial_args(c, p, level);
+    SpatialArgs a = spatial_args(c, p, level);
+    const bool prefilter = p->variance_prefilter == SVGF_VARIANCE_PREFILTER_GAUSS3;
+    if (prefilter) {
+        // blurred variance of this level's input, read by the level kernel for the centre pixel only
+        if (!c->var_blur) SVGF_CUDA(c, cudaMalloc(&c->var_blur, (size_t)c->W * c->H * sizeof(float)));
+        const dim3 g((c->W + 29) / 30, (c->H + 7) / 8);
+        variance_gauss3_kernel<F32><<<g, 256, 0, s>>>(c->W, c->H, (const CT *)in, c->var_blur);
+        c->launches++;
+        SVGF_CUDA(c, cudaGetLastError());
+        a.var_blur = c->var_blur;
+    }
     // tiled fast path: levels 0..4, series-mode normal term (phi_normal >= 32), phi_depth > 0 (null texels rely on
     // |z - inf| * kZ = inf); anything else runs the per-pixel kernel
     // (the bulk copies need 16-byte-aligned row segments: even width for the 8-byte fp16 texels)
@@ -207,14 +221,15 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
         AtrousTiledArgs t;
         t.W = c->W; t.H = c->H; t.level = level; t.tiles_x = t.tiles_y = 0;
         t.uniform_tiles = (p->flags & SVGF_FLAG_NO_UNIFORM_TILES) ? 0 : 1;
+        t.var_blur = a.var_blur;
         t.kL_scale = kLog2e / p->phi_colour;
         t.kZ_scale = kLog2e / ((float)(1 << level) * p->phi_depth);
         t.k1 = a.nt.k1; t.k2 = a.nt.k2; t.k3 = a.nt.k3; t.k4 = a.nt.k4; t.k5 = a.nt.k5;
         // default: packed FP32x2 kernel (needs an even width and 16-byte-aligned planes for its pair loads/stores);
         // SVGF_ATROUS_VARIANT=bulk selects the persistent bulk-copy (UBLKCP) scalar kernel for A/B measurements
         static const char *variant = getenv("SVGF_ATROUS_VARIANT");
-        const bool want_bulk = variant && !strcmp(variant, "bulk");
-        const bool want_stream = variant && !strcmp(variant, "stream");
+        const bool want_bulk = variant && !strcmp(variant, "bulk") && !prefilter;      // the A/B variants have no prefilter path
+        const bool want_stream = variant && !strcmp(variant, "stream") && !prefilter;
         const bool pair_ok = c->W % 2 == 0 && ((uintptr_t)out % 16) == 0 && (!hist_colour || ((uintptr_t)hist_colour % 16) == 0);
         // default: packed FP32x2 tiled kernel.  SVGF_ATROUS_VARIANT=stream selects the warp-specialised streaming kernel
         // (register sliding window; a third of the shared-memory traffic but two consumer warps per sub-partition —
@@ -233,7 +248,8 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
             const int terms = p->phi_normal >= 100.0f ? 4 : 5;
             return F32 ? atrous_packed_f32(c, terms, 3, t, guide_slot, in, out, hist_colour, s) : atrous_packed_f16(c, terms, 3, t, guide_slot, in, out, hist_colour, s);
         }
-        return atrous_tiled(c, F32, p->phi_normal >= 100.0f ? 4 : 5, t, guide_slot, in, out, hist_colour, s);
+        if (!prefilter) return atrous_tiled(c, F32, p->phi_normal >= 100.0f ? 4 : 5, t, guide_slot, in, out, hist_colour, s);
+        // prefilter with planes the packed kernel cannot take: the per-pixel kernel below
     }
     if (a.nt.series)
         atrous_kernel<F32, true><<<grid_for(c), 256, 0, s>>>(a, c->guide[guide_slot], (const CT *)in, (CT *)out, (CT *)hist_colour);
@@ -350,6 +366,7 @@ void svgf_destroy(svgf_ctx *c) {
     cudaFree(c->hist_shadow);
     cudaFree(c->worklist);
     cudaFree(c->work_counter);
+    cudaFree(c->var_blur);
     for (int k = 0; k < 2; k++) { cudaFree(c->guide[k].n); cudaFree(c->guide[k].dz); cudaFree(c->guide[k].mid); }
     if (c->prof_ev) {
         for (int i = 0; i < svgf_ctx::kMaxProf * 4; i++) cudaEventDestroy(c->prof_ev[i]);

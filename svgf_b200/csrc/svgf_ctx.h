@@ -18,6 +18,7 @@ struct svgf_ctx {
     int num_sms = 148;
     unsigned int *worklist = nullptr;     // indices of short-history pixels queued by the fused temporal pass
     unsigned int *work_counter = nullptr;
+    float *var_blur = nullptr;            // 3x3-blurred variance of the current a-trous input (GAUSS3 prefilter), allocated on first use
     const void *guide_key[2] = {nullptr, nullptr};  // motion_depth pointer of the G-buffer each plane was built from
     int guide_cur = 0;                    // slot of the most recently built guide
     bool force_fail_next = false;         // set by svgf_reset

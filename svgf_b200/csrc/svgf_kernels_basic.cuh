@@ -142,7 +142,28 @@ struct SpatialArgs {
     float phi_colour, phi_depth;
     NormalTerm nt;
     int step, level;
+    const float *var_blur;   // a-trous: 3x3-blurred variance of the level's input (SVGF_VARIANCE_PREFILTER_GAUSS3) or nullptr
 };
+
+// ---- SVGF_VARIANCE_PREFILTER_GAUSS3 (include/svgf.h): the [0,1]-clamped variance channel of one plane blurred with
+// (1 2 1; 2 4 2; 1 2 1) / 16, coordinates clamped to the image.  One warp produces 30 pixels of one row: every lane
+// combines rows y-1, y, y+1 of its own column (lanes 0 and 31 carry the neighbour columns), the horizontal pass is two
+// warp shuffles.  The weights are powers of two, so the only roundings are the four additions, in the oracle's order.
+template <bool F32>
+__global__ void __launch_bounds__(256)
+variance_gauss3_kernel(int W, int H, const typename ColourPlane<F32>::texel *__restrict__ in, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (y >= H) return;                                   // uniform per warp
+    const int x = blockIdx.x * 30 + lane - 1;
+    const int px = min(max(x, 0), W - 1), ym = max(y - 1, 0), yp = min(y + 1, H - 1);
+    const float a = clamp01(ColourPlane<F32>::decode(__ldg(in + (size_t)ym * W + px)).w);
+    const float b = clamp01(ColourPlane<F32>::decode(__ldg(in + (size_t)y * W + px)).w);
+    const float c = clamp01(ColourPlane<F32>::decode(__ldg(in + (size_t)yp * W + px)).w);
+    const float col = __fadd_rn(__fadd_rn(0.25f * a, 0.5f * b), 0.25f * c);
+    const float l = __shfl_up_sync(0xffffffffu, col, 1), r = __shfl_down_sync(0xffffffffu, col, 1);
+    if (lane >= 1 && lane <= 30 && x < W) out[(size_t)y * W + x] = __fadd_rn(__fadd_rn(0.25f * l, 0.5f * col), 0.25f * r);
+}
 
 // ---- variance estimation: reference filter::FilterMoments (src/Filter.cuh:430-525) -------------------------
 // 7x7 cross-bilateral estimate for one short-history pixel (:446-516)
@@ -241,7 +262,8 @@ atrous_kernel(SpatialArgs a, Guide guide, const typename ColourPlane<F32>::texel
     }
     const float lc = luminance(c.x, c.y, c.z);
     const float3 nc = guide_normal(gc);
-    const float phiL = a.phi_colour * sqrtf(fmaxf(0.0f, 1e-10f + c.w));        // :562
+    const float var = a.var_blur ? __ldg(a.var_blur + i) : c.w;
+    const float phiL = a.phi_colour * sqrtf(fmaxf(0.0f, 1e-10f + var));        // :562
     const float kL = kLog2e / phiL;
     const float phiZ = fmaxf(__ldg(guide.dz + i), 1e-6f) * (float)a.step * a.phi_depth;  // :563
     const float kZ1 = (phiZ == 0.0f) ? 0.0f : kLog2e / phiZ;

@@ -313,7 +313,9 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
         live0[j] = inside && (g0.x != kBackgroundZ);                               // :554: background passes through
         live1[j] = inside && (g0.y != kBackgroundZ);
         any_live |= live0[j] | live1[j];
-        C[j].kL = make_float2(a.kL_scale * rsqrtf(1e-10f + c1.z), a.kL_scale * rsqrtf(1e-10f + c1.w));   // :562
+        float2 var = make_float2(c1.z, c1.w);                                       // :547 / the pre-blurred plane (GAUSS3)
+        if (a.var_blur && inside) var = __ldg(reinterpret_cast<const float2 *>(a.var_blur + (size_t)gy * a.W + gx));
+        C[j].kL = make_float2(a.kL_scale * rsqrtf(1e-10f + var.x), a.kL_scale * rsqrtf(1e-10f + var.y));   // :562
         float2 dz = make_float2(0.f, 0.f);
         if (inside) dz = __ldg(reinterpret_cast<const float2 *>(guide_dz + (size_t)gy * a.W + gx));
         C[j].kZ = make_float2(__fdividef(a.kZ_scale, fmaxf(dz.x, 1e-6f)), __fdividef(a.kZ_scale, fmaxf(dz.y, 1e-6f)));   // :563

@@ -48,6 +48,7 @@ struct AtrousTiledArgs {
     int level;
     int tiles_x, tiles_y;       // tiles_y counts (row block, phase) pairs
     int uniform_tiles;          // packed kernel: allow the uniform-normal tile shortcut
+    const float *var_blur;      // packed kernel: blurred variance plane (SVGF_VARIANCE_PREFILTER_GAUSS3) or nullptr
 };
 
 // -log2 of the reference's tap kernel KW[|xx|] * KW[|yy|], KW = {1, 2/3, 1/6} as floats (src/Filter.cuh:540,582):

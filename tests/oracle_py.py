@@ -119,6 +119,11 @@ def atrous(p, g, inp, level, hist_colour=None):
             c = [clamp01(float(v)) for v in inp[y, x]]
             lc = lum(c)
             var = c[3]
+            if getattr(p, "variance_prefilter", 0) == 1:     # SVGF_VARIANCE_PREFILTER_GAUSS3: (1 2 1; 2 4 2; 1 2 1) / 16, clamped coordinates
+                var = 0.0
+                for dy, wy in ((-1, 0.25), (0, 0.5), (1, 0.25)):
+                    for dx, wx in ((-1, 0.25), (0, 0.5), (1, 0.25)):
+                        var += wy * wx * clamp01(float(inp[min(max(y + dy, 0), H - 1), min(max(x + dx, 0), W - 1), 3]))
             zc, dzc = depth(g["motion"], x, y)
             if zc == 1e30:
                 out[y, x] = c

@@ -280,6 +280,53 @@ def test_agrees_with_independent_python_restatement(seed):
             assert rel_err(hc, hc_py, 1e-3) < 2e-4
 
 
+@pytest.mark.parametrize("seed", [3, 4])
+def test_variance_prefilter_agrees_with_independent_python_restatement(seed):
+    """SVGF_VARIANCE_PREFILTER_GAUSS3 (include/svgf.h; the SVGF paper's 3x3 variance blur, absent from the reference)."""
+    rng = np.random.default_rng(seed)
+    W, H = 12, 9
+    cur = random_scene(rng, W, H, storage="f32")
+    p = default_params()
+    p.variance_prefilter = 1
+    of = _mk(W, H, params=p)
+    of.PingPongInx = 0
+    of.set_inputs(cur)
+    a_in = rng.uniform(0, 1.1, size=(H, W, 4)).astype(np.float32)
+    a_in[..., 3] = rng.uniform(1e-2, 0.3, size=(H, W)).astype(np.float32)
+    a_in[rng.uniform(size=(H, W)) < 0.3, 3] = 0.9          # strong variance contrast: the blur must matter
+    g = of.gbuf(0)
+    plain = default_params()
+    for level in (0, 1, 2):
+        out = np.zeros_like(a_in); out_plain = np.zeros_like(a_in)
+        hc = of.RenderBuffer[0].copy()
+        assert oracle().svgf_oracle_atrous_level(C.byref(p), W, H, 1, C.byref(g), a_in.ctypes.data, out.ctypes.data, hc.ctypes.data, level) == 0
+        assert oracle().svgf_oracle_atrous_level(C.byref(plain), W, H, 1, C.byref(g), a_in.ctypes.data, out_plain.ctypes.data, hc.ctypes.data, level) == 0
+        o_py, _ = oracle_py.atrous(p, decode_gbuf(cur), a_in, level, None)
+        assert rel_err(out[..., :3], o_py[..., :3], 1e-3) < 2e-5, level
+        assert rel_err(out[..., 3], o_py[..., 3], 1e-4) < 2e-4, level
+        assert np.abs(out - out_plain).max() > 1e-3, "the prefilter changed nothing"
+
+
+def test_variance_prefilter_of_a_constant_variance_plane_is_the_identity():
+    rng = np.random.default_rng(9)
+    W, H = 16, 8
+    cur = random_scene(rng, W, H, storage="f16")
+    a_in = rng.uniform(0, 1, size=(H, W, 4)).astype(np.float16)
+    a_in[..., 3] = np.float16(0.125)                        # exactly representable: the blur returns it exactly
+    outs = []
+    for mode in (0, 1):
+        p = default_params()
+        p.variance_prefilter = mode
+        of = _mk(W, H, storage="f16", params=p)
+        of.set_inputs(cur)
+        g = of.gbuf(0)
+        out = np.zeros_like(a_in)
+        hc = of.RenderBuffer[0].copy()
+        assert oracle().svgf_oracle_atrous_level(C.byref(p), W, H, 0, C.byref(g), a_in.ctypes.data, out.ctypes.data, hc.ctypes.data, 1) == 0
+        outs.append(out)
+    assert np.array_equal(outs[0].view(np.uint16), outs[1].view(np.uint16))
+
+
 def test_argument_validation():
     of = _mk(4, 4)
     of.params.history_cap = 0
