@@ -160,6 +160,8 @@ def run_ours(args, rank, world, local):
     f = SvgfFilter(W, H, device=dev, storage=args.storage)
     f.SpatialFilterSteps = args.levels
     f.params.flags = args.flags
+    f.params.variance_prefilter = args.prefilter
+    f.params.reproj_mode = args.reproj
     lib = f.lib
     stream = torch.cuda.current_stream(dev)
     sptr = C.c_void_p(stream.cuda_stream)
@@ -262,7 +264,8 @@ def run_ours(args, rank, world, local):
                                + (f"; {world} independent streams, one per GPU" if world > 1 else ""),
                    "width": W, "height": H, "atrous_levels": n_levels, "storage": args.storage, "frames_resident": R,
                    "l2": "every step reads a fresh frame (%.0f MB of inputs > 126 MB L2)" % (IN_BYTES_PER_PX[args.storage] * W * H / 1e6),
-                   "params": "reference defaults (history 24, depth 0.8, normal 0.9, phi colour 10, phi normal 128)", "flags": args.flags},
+                   "params": "reference defaults (history 24, depth 0.8, normal 0.9, phi colour 10, phi normal 128)", "flags": args.flags,
+                   "variance_prefilter": args.prefilter, "reproj_mode": args.reproj},
         "e2e": {"value": round(e2e_value, 4), "unit": "Gpix/s", "h2d_bytes_per_step": IN_BYTES_PER_PX[args.storage] * W * H,
                 "d2h_bytes_per_step": OUT_BYTES_PER_PX[args.storage] * W * H, "ms_per_step": round(e2e_ms / Ke, 4), "steps": Ke,
                 "api": "svgf_frame_host (pinned host buffers; copy-in, kernels and copy-out of consecutive frames overlap on three streams; timed region starts with the pipeline drained)", "result_checksum": checksum},
@@ -491,6 +494,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--cpu-budget-px", type=float, default=1.6e6, help="pixels per frame of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prefilter", type=int, default=0, help="svgf_params.variance_prefilter (1 = 3x3 Gaussian, not in the reference)")
+    ap.add_argument("--reproj", type=int, default=0, help="svgf_params.reproj_mode (1 = bilinear 2x2, not in the reference)")
     ap.add_argument("--flags", type=int, default=0, help="svgf_params.flags for A/B runs (8 = no uniform-normal tile shortcut)")
     ap.add_argument("--band-balance", type=int, default=1, help="--mode bands: 1 = band heights balanced by estimated work (background rows are cheap), 0 = equal heights")
     ap.add_argument("--band-bg-cost", type=float, default=0.2, help="--mode bands: cost of a background pixel relative to a filtered one")

@@ -55,8 +55,14 @@ typedef enum svgf_storage { SVGF_STORE_F16 = 0, SVGF_STORE_F32 = 1 } svgf_storag
  * (both ids read as denormals -> 0 -> the test always passes). */
 typedef enum svgf_mesh_id_mode { SVGF_MESH_ID_INTENDED = 0, SVGF_MESH_ID_REFERENCE_VACUOUS = 1 } svgf_mesh_id_mode;
 
-/* History fetch.  NEAREST_TRUNC is what the reference does (src/Filter.cuh:231-232). */
-typedef enum svgf_reproj_mode { SVGF_REPROJ_NEAREST_TRUNC = 0 } svgf_reproj_mode;
+/* History fetch.  NEAREST_TRUNC is what the reference does (src/Filter.cuh:231-232: one texel at
+ * coord + ivec2(motion), C truncation).  BILINEAR is the SVGF paper's form, which the reference leaves out: the four
+ * texels around p = coord + motion (x0 = floor(p.x), y0 = floor(p.y)), visited in the order (x0,y0) (x0+1,y0) (x0,y0+1)
+ * (x0+1,y0+1), each subjected to the reference's own consistency tests (inside the image, depth, mesh id, normal;
+ * src/Filter.cuh:235-252) against the current pixel; colour, moments and history length are the bilinear-weighted
+ * means over the texels that pass (sum of w*v divided by sum of w, FP32, in that order); the reprojection fails when
+ * the passing weights sum to less than 0.01.  The fetched history length is int(mean + 0.5). */
+typedef enum svgf_reproj_mode { SVGF_REPROJ_NEAREST_TRUNC = 0, SVGF_REPROJ_BILINEAR = 1 } svgf_reproj_mode;
 
 /* Variance pre-filter of the a-trous levels.  NONE is what the reference does (src/Filter.cuh:547,562: the centre
  * texel's own variance scales the luminance edge-stopping term).  GAUSS3 is the SVGF paper's form, which the reference

@@ -182,7 +182,7 @@ int check_common(const svgf_params *p, int W, int H, int storage) {
     if (storage != SVGF_STORE_F16 && storage != SVGF_STORE_F32) return SVGF_INVALID_ARG;
     if (p->history_cap < 1 || p->history_cap > 255) return SVGF_INVALID_ARG;  // D9
     if (p->atrous_iterations < 0 || p->atrous_iterations > 10) return SVGF_INVALID_ARG;
-    if (p->reproj_mode != SVGF_REPROJ_NEAREST_TRUNC) return SVGF_UNSUPPORTED;
+    if (p->reproj_mode != SVGF_REPROJ_NEAREST_TRUNC && p->reproj_mode != SVGF_REPROJ_BILINEAR) return SVGF_UNSUPPORTED;
     if (p->variance_prefilter != SVGF_VARIANCE_PREFILTER_NONE && p->variance_prefilter != SVGF_VARIANCE_PREFILTER_GAUSS3)
         return SVGF_UNSUPPORTED;
     return SVGF_OK;
@@ -202,26 +202,58 @@ void temporal(const svgf_params &P, int W, int H, const GBuf &cur, const GBuf &p
             V2 pm = {0, 0};
             int h = 1;
             bool ok = false;
-            {
-                const float *mv = cur.mot(x, y);                                     // :230
+            // the reference's consistency tests for one previous-frame texel (src/Filter.cuh:235-252)
+            auto consistent = [&](int qx, int qy) {
+                if (qx < 0 || qx >= W || qy < 0 || qy >= H) return false;            // :235
+                const V2 dc = cur.depth(x, y);                                       // :239
+                const V2 dp = prev.depth(qx, qy);                                    // :240
+                if (fabsf(dp.x - dc.x) > P.depth_threshold) return false;            // :242
+                if (cur.mesh_id(x, y, P.mesh_id_mode) != prev.mesh_id(qx, qy, P.mesh_id_mode)) return false;  // :245-247
+                const V3 n0 = cur.nrm(x, y), n1 = prev.nrm(qx, qy);                  // :250-251
+                return !(dot3(n0, n1) < P.normal_threshold);                         // :252
+            };
+            const float *mv = cur.mot(x, y);                                         // :230
+            if (P.reproj_mode == SVGF_REPROJ_BILINEAR) {
+                // SVGF_REPROJ_BILINEAR (include/svgf.h; the paper's 2x2 fetch, not in the reference)
+                const float fxp = (float)x + mv[0], fyp = (float)y + mv[1];
+                if (fabsf(fxp) < 1e8f && fabsf(fyp) < 1e8f) {                        // false for NaN
+                    const float flx = floorf(fxp), fly = floorf(fyp);
+                    const float tx = fxp - flx, ty = fyp - fly;
+                    const int x0 = (int)flx, y0 = (int)fly;
+                    const float wx[2] = {1.0f - tx, tx}, wy[2] = {1.0f - ty, ty};
+                    float ws = 0.0f, hs = 0.0f;
+                    V3 cs = {0, 0, 0};
+                    V2 ms = {0, 0};
+                    for (int j = 0; j < 2; j++)
+                        for (int k = 0; k < 2; k++) {
+                            const int qx = x0 + k, qy = y0 + j;
+                            if (!consistent(qx, qy)) continue;
+                            const float w = wx[k] * wy[j];
+                            const size_t qi = (size_t)qy * W + qx;
+                            const V4 p4 = Colour<F32>::ld01(prev_colour, qi);
+                            const V2 m2 = Moments<F32>::raw(prev_mom, qi);
+                            ws += w;
+                            cs.x += w * p4.x; cs.y += w * p4.y; cs.z += w * p4.z;
+                            ms.x += w * m2.x; ms.y += w * m2.y;
+                            hs += w * (float)hprev[qi];
+                        }
+                    if (ws >= 0.01f) {
+                        pc = {cs.x / ws, cs.y / ws, cs.z / ws};
+                        pm = {ms.x / ws, ms.y / ws};
+                        h = (int)(hs / ws + 0.5f);
+                        ok = true;
+                    }
+                }
+            } else {
                 const int qx = x + f2i_rz(mv[0]);                                    // :232 ivec2(vec2) truncation
                 const int qy = y + f2i_rz(mv[1]);
-                if (!(qx < 0 || qx >= W || qy < 0 || qy >= H)) {                     // :235
-                    const V2 dc = cur.depth(x, y);                                   // :239
-                    const V2 dp = prev.depth(qx, qy);                                // :240
-                    if (!(fabsf(dp.x - dc.x) > P.depth_threshold)) {                 // :242
-                        if (cur.mesh_id(x, y, P.mesh_id_mode) == prev.mesh_id(qx, qy, P.mesh_id_mode)) {  // :245-247
-                            const V3 n0 = cur.nrm(x, y), n1 = prev.nrm(qx, qy);      // :250-251
-                            if (!(dot3(n0, n1) < P.normal_threshold)) {              // :252
-                                const size_t qi = (size_t)qy * W + qx;
-                                const V4 p4 = Colour<F32>::ld01(prev_colour, qi);    // :254
-                                pc = {p4.x, p4.y, p4.z};
-                                h = (int)hprev[qi];                                  // :255
-                                pm = Moments<F32>::raw(prev_mom, qi);                // :256
-                                ok = true;
-                            }
-                        }
-                    }
+                if (consistent(qx, qy)) {
+                    const size_t qi = (size_t)qy * W + qx;
+                    const V4 p4 = Colour<F32>::ld01(prev_colour, qi);                // :254
+                    pc = {p4.x, p4.y, p4.z};
+                    h = (int)hprev[qi];                                              // :255
+                    pm = Moments<F32>::raw(prev_mom, qi);                            // :256
+                    ok = true;
                 }
             }
             float alpha, alpha_m;

@@ -28,7 +28,7 @@ svgf_status check_params(const svgf_params *p) {
     if (!(p->alpha_min >= 0.0f && p->alpha_min <= 1.0f) || !(p->moments_alpha_min >= 0.0f && p->moments_alpha_min <= 1.0f))
         return SVGF_INVALID_ARG;
     if (p->mesh_id_mode != SVGF_MESH_ID_INTENDED && p->mesh_id_mode != SVGF_MESH_ID_REFERENCE_VACUOUS) return SVGF_INVALID_ARG;
-    if (p->reproj_mode != SVGF_REPROJ_NEAREST_TRUNC) return SVGF_UNSUPPORTED;
+    if (p->reproj_mode != SVGF_REPROJ_NEAREST_TRUNC && p->reproj_mode != SVGF_REPROJ_BILINEAR) return SVGF_UNSUPPORTED;
     if (p->variance_prefilter != SVGF_VARIANCE_PREFILTER_NONE && p->variance_prefilter != SVGF_VARIANCE_PREFILTER_GAUSS3)
         return SVGF_UNSUPPORTED;
     return SVGF_OK;
@@ -109,14 +109,14 @@ svgf_status launch_temporal(svgf_ctx *c, const svgf_params *p, const svgf_gbuffe
     int cur_slot = (prev_slot >= 0) ? 1 - prev_slot : 1 - c->guide_cur;
     if (c->guide_key[cur_slot] == prev->motion_depth) c->guide_key[cur_slot] = nullptr;
     const dim3 grid = grid_for(c);
-    if (prev_slot >= 0)
-        temporal_kernel<F32, true><<<grid, 256, 0, s>>>(a, view(c, cur), view(c, prev), c->guide[prev_slot], c->guide[cur_slot],
-                                                        (const CT *)prev_colour, (CT *)cur_colour, hist_prev, hist_out,
-                                                        (MT *)cur_mom, (const MT *)prev_mom, fused);
-    else
-        temporal_kernel<F32, false><<<grid, 256, 0, s>>>(a, view(c, cur), view(c, prev), Guide{nullptr, nullptr, nullptr}, c->guide[cur_slot],
-                                                         (const CT *)prev_colour, (CT *)cur_colour, hist_prev, hist_out,
-                                                         (MT *)cur_mom, (const MT *)prev_mom, fused);
+    const Guide pg = (prev_slot >= 0) ? c->guide[prev_slot] : Guide{nullptr, nullptr, nullptr};
+#define SVGF_LAUNCH_TEMPORAL(PG, BL)                                                                                              \
+    temporal_kernel<F32, PG, BL><<<grid, 256, 0, s>>>(a, view(c, cur), view(c, prev), pg, c->guide[cur_slot], (const CT *)prev_colour, \
+                                                      (CT *)cur_colour, hist_prev, hist_out, (MT *)cur_mom, (const MT *)prev_mom, fused)
+    const bool bilinear = p->reproj_mode == SVGF_REPROJ_BILINEAR;
+    if (prev_slot >= 0) { if (bilinear) SVGF_LAUNCH_TEMPORAL(true, true); else SVGF_LAUNCH_TEMPORAL(true, false); }
+    else { if (bilinear) SVGF_LAUNCH_TEMPORAL(false, true); else SVGF_LAUNCH_TEMPORAL(false, false); }
+#undef SVGF_LAUNCH_TEMPORAL
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
     c->guide_key[cur_slot] = cur->motion_depth;

@@ -53,7 +53,10 @@ __global__ void __launch_bounds__(256) build_guide_kernel(GBufView g, Guide guid
 // ---- temporal reprojection + accumulation: reference filter::TemporalFilter (src/Filter.cuh:359-404) with
 // LoadPreviousData (:225-258).  PREV_GUIDE: previous-frame consistency data comes from the compact guide
 // plane cached by the previous frame instead of the three previous G-buffer planes.
-template <bool F32, bool PREV_GUIDE>
+// BILINEAR: SVGF_REPROJ_BILINEAR (include/svgf.h) - the 2x2 texels around coord + motion, each under the same consistency
+// tests, weighted means of colour / moments / history length over the texels that pass; un-contracted FP32 in the
+// oracle's order so that the fetched history length rounds identically.
+template <bool F32, bool PREV_GUIDE, bool BILINEAR = false>
 __global__ void __launch_bounds__(256)
 temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, Guide prev_guide, Guide cur_guide, const typename ColourPlane<F32>::texel *__restrict__ prev_colour,
                 typename ColourPlane<F32>::texel *colour, const uint8_t *__restrict__ hist_prev, uint8_t *__restrict__ hist_out,
@@ -74,8 +77,9 @@ temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, Guide prev_guide, G
     float2 pm = make_float2(0.f, 0.f);
     int h = 1;
     bool ok = false;
-    const int qx = x + __float2int_rz(mv.x), qy = y + __float2int_rz(mv.y);    // :232
-    if (!a.force_fail && qx >= 0 && qx < a.W && qy >= 0 && qy < a.H) {         // :235
+    // the reference's consistency tests for one previous-frame texel (:235-252)
+    auto consistent = [&](int qx, int qy) -> bool {
+        if (qx < 0 || qx >= a.W || qy < 0 || qy >= a.H) return false;          // :235
         const size_t qi = (size_t)qy * a.W + qx;
         float4 pn;
         unsigned short pmid;
@@ -86,14 +90,52 @@ temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, Guide prev_guide, G
             const GuideTexel pg = make_guide(prev.mot(qx, qy), prev.nrm(qx, qy), prev.uvw(qx, qy));
             pn = pg.n; pmid = pg.mid;
         }
-        ok = !(fabsf(pn.x - g.n.x) > a.depth_threshold);                       // :242
-        ok = ok && (a.vacuous_mesh_id || guide_mesh_id(g.mid) == guide_mesh_id(pmid));  // :245-247
-        ok = ok && !(dot3(guide_normal(g.n), guide_normal(pn)) < a.normal_threshold);  // :250-252
-        if (ok) {
+        bool good = !(fabsf(pn.x - g.n.x) > a.depth_threshold);                // :242
+        good = good && (a.vacuous_mesh_id || guide_mesh_id(g.mid) == guide_mesh_id(pmid));  // :245-247
+        return good && !(dot3(guide_normal(g.n), guide_normal(pn)) < a.normal_threshold);  // :250-252
+    };
+    if (BILINEAR) {
+        const float fxp = __fadd_rn((float)x, mv.x), fyp = __fadd_rn((float)y, mv.y);
+        if (!a.force_fail && fabsf(fxp) < 1e8f && fabsf(fyp) < 1e8f) {         // false for NaN
+            const float flx = floorf(fxp), fly = floorf(fyp);
+            const float tx = __fsub_rn(fxp, flx), ty = __fsub_rn(fyp, fly);
+            const int x0 = (int)flx, y0 = (int)fly;
+            const float wx[2] = {__fsub_rn(1.0f, tx), tx}, wy[2] = {__fsub_rn(1.0f, ty), ty};
+            float ws = 0.0f, hs = 0.0f;
+            float3 cs = make_float3(0.f, 0.f, 0.f);
+            float2 ms = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const int qx = x0 + k, qy = y0 + j;
+                    if (!consistent(qx, qy)) continue;
+                    const float w = __fmul_rn(wx[k], wy[j]);
+                    const size_t qi = (size_t)qy * a.W + qx;
+                    const float4 p4 = clamp01(ColourPlane<F32>::decode(__ldg(prev_colour + qi)));
+                    const float2 m2 = MomentsPlane<F32>::decode(__ldg(prev_mom + qi));
+                    ws = __fadd_rn(ws, w);
+                    cs.x = __fadd_rn(cs.x, __fmul_rn(w, p4.x)); cs.y = __fadd_rn(cs.y, __fmul_rn(w, p4.y));
+                    cs.z = __fadd_rn(cs.z, __fmul_rn(w, p4.z));
+                    ms.x = __fadd_rn(ms.x, __fmul_rn(w, m2.x)); ms.y = __fadd_rn(ms.y, __fmul_rn(w, m2.y));
+                    hs = __fadd_rn(hs, __fmul_rn(w, (float)hist_prev[qi]));
+                }
+            if (ws >= 0.01f) {
+                pc = make_float3(__fdiv_rn(cs.x, ws), __fdiv_rn(cs.y, ws), __fdiv_rn(cs.z, ws));
+                pm = make_float2(__fdiv_rn(ms.x, ws), __fdiv_rn(ms.y, ws));
+                h = (int)__fadd_rn(__fdiv_rn(hs, ws), 0.5f);
+                ok = true;
+            }
+        }
+    } else {
+        const int qx = x + __float2int_rz(mv.x), qy = y + __float2int_rz(mv.y);    // :232
+        if (!a.force_fail && consistent(qx, qy)) {
+            const size_t qi = (size_t)qy * a.W + qx;
             const float4 p4 = clamp01(ColourPlane<F32>::decode(__ldg(prev_colour + qi)));  // :254
             pc = make_float3(p4.x, p4.y, p4.z);
             h = hist_prev[qi];                                                 // :255 (snapshot plane)
             pm = MomentsPlane<F32>::decode(__ldg(prev_mom + qi));              // :256
+            ok = true;
         }
     }
     float alpha = 1.0f, alpha_m = 1.0f;

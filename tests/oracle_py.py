@@ -48,21 +48,45 @@ def temporal(p, cur, prev, prev_col, cur_col, hist, prev_mom):
         for x in range(W):
             c = [clamp01(float(v)) for v in cur_col[y, x, :3]]
             mv = cur["motion"][y, x]
-            qx, qy = x + int(mv[0]), y + int(mv[1])  # int() truncates toward zero
-            ok = 0 <= qx < W and 0 <= qy < H
-            if ok:
-                ok = not (abs(depth(prev["motion"], qx, qy)[0] - depth(cur["motion"], x, y)[0]) > p.depth_threshold)
-            if ok and p.mesh_id_mode == 0:
-                ok = int(cur["inst"][y, x]) == int(prev["inst"][qy, qx])
-            if ok:
+
+            def consistent(qx, qy):
+                if not (0 <= qx < W and 0 <= qy < H):
+                    return False
+                if abs(depth(prev["motion"], qx, qy)[0] - depth(cur["motion"], x, y)[0]) > p.depth_threshold:
+                    return False
+                if p.mesh_id_mode == 0 and int(cur["inst"][y, x]) != int(prev["inst"][qy, qx]):
+                    return False
                 a, b = nrm(cur["normal"], x, y), nrm(prev["normal"], qx, qy)
-                ok = not ((a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) < p.normal_threshold)
-            if ok:
-                pc = [clamp01(float(v)) for v in prev_col[qy, qx, :3]]
-                h = min(p.history_cap, int(hist[qy, qx]) + 1)
-                pm = [float(v) for v in prev_mom[qy, qx]]
-                alpha = f32(1.0 / h)
+                return not ((a[0] * b[0] + a[1] * b[1] + a[2] * b[2]) < p.normal_threshold)
+
+            if getattr(p, "reproj_mode", 0) == 1:      # SVGF_REPROJ_BILINEAR (include/svgf.h), float64 here
+                fx, fy = f32(f32(x) + f32(mv[0])), f32(f32(y) + f32(mv[1]))
+                x0, y0 = math.floor(fx), math.floor(fy)
+                tx, ty = fx - x0, fy - y0
+                ws, hs, cs, ms = 0.0, 0.0, [0.0] * 3, [0.0] * 2
+                for j, wy in ((0, 1 - ty), (1, ty)):
+                    for k, wx in ((0, 1 - tx), (1, tx)):
+                        qx, qy = x0 + k, y0 + j
+                        if consistent(qx, qy):
+                            w = wx * wy
+                            ws += w
+                            hs += w * int(hist[qy, qx])
+                            cs = [cs[n] + w * clamp01(float(prev_col[qy, qx, n])) for n in range(3)]
+                            ms = [ms[n] + w * float(prev_mom[qy, qx, n]) for n in range(2)]
+                ok = ws >= 0.01
+                if ok:
+                    pc, pm = [v / ws for v in cs], [v / ws for v in ms]
+                    h = min(p.history_cap, int(hs / ws + 0.5) + 1)
+                    alpha = f32(1.0 / h)
             else:
+                qx, qy = x + int(mv[0]), y + int(mv[1])  # int() truncates toward zero
+                ok = consistent(qx, qy)
+                if ok:
+                    pc = [clamp01(float(v)) for v in prev_col[qy, qx, :3]]
+                    h = min(p.history_cap, int(hist[qy, qx]) + 1)
+                    pm = [float(v) for v in prev_mom[qy, qx]]
+                    alpha = f32(1.0 / h)
+            if not ok:
                 pc, pm, h, alpha = [0, 0, 0], [0, 0], 1, 1.0
             L = lum(c)
             m = [pm[0] * (1 - alpha) + L * alpha, pm[1] * (1 - alpha) + L * L * alpha]

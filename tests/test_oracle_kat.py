@@ -327,6 +327,73 @@ def test_variance_prefilter_of_a_constant_variance_plane_is_the_identity():
     assert np.array_equal(outs[0].view(np.uint16), outs[1].view(np.uint16))
 
 
+@pytest.mark.parametrize("seed", [5, 6, 7])
+def test_bilinear_reprojection_agrees_with_independent_python_restatement(seed):
+    """SVGF_REPROJ_BILINEAR (include/svgf.h; the SVGF paper's 2x2 history fetch, absent from the reference)."""
+    rng = np.random.default_rng(seed)
+    W, H = 13, 10
+    cur = random_scene(rng, W, H, storage="f32")
+    prev = random_scene(rng, W, H, storage="f32")
+    keep = rng.uniform(size=(H, W)) < 0.75
+    for k in ("normal", "uv"):
+        prev[k][keep] = cur[k][keep]
+    prev["motion"][keep, 2:] = cur["motion"][keep, 2:]
+    # fractional motion away from .0 / .5 (the fp64 restatement must pick the same texels and the same rounded length)
+    cur["motion"][..., :2] = (rng.integers(-2, 3, size=(H, W, 2)) + rng.choice([0.13, 0.31, 0.71, 0.88], size=(H, W, 2))).astype(np.float32)
+    p = default_params()
+    p.history_cap = 9
+    p.reproj_mode = 1
+    of = _mk(W, H, params=p)
+    of.PingPongInx = 0
+    of.set_inputs(cur)
+    of.normal[1][...] = prev["normal"]; of.uv[1][...] = prev["uv"]; of.motion[1][...] = prev["motion"]
+    of.RenderBuffer[1][...] = rng.uniform(0, 1.2, size=(H, W, 4)).astype(np.float32)
+    of.MomentsBuffer[1][...] = rng.uniform(0, 1, size=(H, W, 2)).astype(np.float32)
+    hist0 = rng.integers(0, 12, size=(H, W)).astype(np.uint8)
+    of.HistoryLengthBuffer[...] = hist0
+    prev_col, prev_mom = of.RenderBuffer[1].copy(), of.MomentsBuffer[1].copy()
+    c_py, h_py, m_py = oracle_py.temporal(p, decode_gbuf(cur), decode_gbuf(prev), prev_col, cur["colour"], hist0, prev_mom)
+    of.TemporalFilter()
+    assert np.array_equal(of.HistoryLengthBuffer, h_py)
+    assert (h_py > 1).mean() > 0.3, "too few successful reprojections to mean anything"
+    assert rel_err(of.RenderBuffer[0][..., :3], c_py[..., :3], 1e-3) < 5e-6
+    assert np.abs(of.RenderBuffer[0][..., 3] - c_py[..., 3]).max() < 1e-6
+    assert rel_err(of.MomentsBuffer[0], m_py, 1e-3) < 1e-5
+    # and it is not the nearest fetch in disguise
+    q = default_params(); q.history_cap = 9
+    on = _mk(W, H, params=q)
+    on.PingPongInx = 0
+    on.set_inputs(cur)
+    on.normal[1][...] = prev["normal"]; on.uv[1][...] = prev["uv"]; on.motion[1][...] = prev["motion"]
+    on.RenderBuffer[1][...] = prev_col; on.MomentsBuffer[1][...] = prev_mom; on.HistoryLengthBuffer[...] = hist0
+    on.TemporalFilter()
+    assert np.abs(on.RenderBuffer[0] - of.RenderBuffer[0]).max() > 1e-2
+
+
+def test_bilinear_reprojection_with_integer_motion_is_the_nearest_fetch():
+    """Integer motion vectors put all the weight on one texel: both modes must then agree bit for bit."""
+    rng = np.random.default_rng(11)
+    W, H = 24, 16
+    cur = random_scene(rng, W, H, storage="f16")
+    cur["motion"][..., :2] = rng.integers(-3, 4, size=(H, W, 2)).astype(np.float32)
+    res = []
+    for mode in (0, 1):
+        p = default_params()
+        p.reproj_mode = mode
+        of = _mk(W, H, storage="f16", params=p)
+        of.PingPongInx = 0
+        of.set_inputs(cur)
+        of.normal[1][...] = of.normal[0]; of.uv[1][...] = of.uv[0]; of.motion[1][...] = of.motion[0]
+        r2 = np.random.default_rng(12)
+        of.RenderBuffer[1][...] = r2.uniform(0, 1, size=(H, W, 4)).astype(np.float16)
+        of.MomentsBuffer[1][...] = r2.uniform(0, 1, size=(H, W, 2)).astype(np.float16)
+        of.HistoryLengthBuffer[...] = r2.integers(0, 30, size=(H, W)).astype(np.uint8)
+        of.TemporalFilter()
+        res.append((of.RenderBuffer[0].copy(), of.MomentsBuffer[0].copy(), of.HistoryLengthBuffer.copy()))
+    for a, b in zip(*res):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
 def test_argument_validation():
     of = _mk(4, 4)
     of.params.history_cap = 0

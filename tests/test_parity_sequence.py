@@ -48,10 +48,12 @@ def _frame_stats(f, o, storage):
     return out
 
 
-def run_sequence(W, H, frames, storage, check_every=1, seed=0, steps=5, teacher_forced=False, variance_prefilter=0):
+def run_sequence(W, H, frames, storage, check_every=1, seed=0, steps=5, teacher_forced=False, variance_prefilter=0, reproj_mode=0, flags=0):
     f = SvgfFilter(W, H, storage=storage)
     o = OracleFilter(W, H, storage=storage)
     f.params.variance_prefilter = o.params.variance_prefilter = variance_prefilter
+    f.params.reproj_mode = o.params.reproj_mode = reproj_mode
+    f.params.flags = flags
     f.SpatialFilterSteps = steps
     o.params.atrous_iterations = steps
     f.Reset(); o.Reset()

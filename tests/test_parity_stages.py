@@ -189,11 +189,16 @@ def test_argument_validation_through_the_abi():
     with pytest.raises(_lib.SvgfError):
         f.TemporalFilter()
     f.params.history_cap = 24
-    f.params.reproj_mode = 1
+    f.params.reproj_mode = 2           # 0 = the reference's truncated nearest fetch, 1 = bilinear; nothing else exists
     with pytest.raises(_lib.SvgfError) as e:
         f.Filter()
     assert e.value.status == _lib.SVGF_UNSUPPORTED
     f.params.reproj_mode = 0
+    f.params.variance_prefilter = 2
+    with pytest.raises(_lib.SvgfError) as e:
+        f.Filter()
+    assert e.value.status == _lib.SVGF_UNSUPPORTED
+    f.params.variance_prefilter = 0
     f.params.atrous_iterations = 11
     with pytest.raises(_lib.SvgfError):
         f.Filter()
