@@ -216,8 +216,9 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
     // tiled fast path: levels 0..4, series-mode normal term (phi_normal >= 32), phi_depth > 0 (null texels rely on
     // |z - inf| * kZ = inf); anything else runs the per-pixel kernel
     // (the bulk copies need 16-byte-aligned row segments: even width for the 8-byte fp16 texels)
+    // (with the variance prefilter only the packed three-term kernel has a fast path: phi_normal >= 100)
     if (level <= 4 && a.nt.series && p->phi_depth > 0.0f && !(p->flags & SVGF_FLAG_BASIC_KERNELS) && (F32 || c->W % 2 == 0) &&
-        ((uintptr_t)in % 16) == 0) {
+        ((uintptr_t)in % 16) == 0 && !(prefilter && p->phi_normal < 100.0f)) {
         AtrousTiledArgs t;
         t.W = c->W; t.H = c->H; t.level = level; t.tiles_x = t.tiles_y = 0;
         t.uniform_tiles = (p->flags & SVGF_FLAG_NO_UNIFORM_TILES) ? 0 : 1;
@@ -237,7 +238,7 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
         if (want_stream && pair_ok)
             return atrous_stream(c, F32, p->phi_normal >= 100.0f ? 4 : 5, t, guide_slot, in, out, hist_colour, s);
         if (!want_bulk && c->W % 2 == 0 && ((uintptr_t)out % 16) == 0 && (!hist_colour || ((uintptr_t)hist_colour % 16) == 0)) {
-            if (p->phi_normal >= 100.0f && !(variant && !strcmp(variant, "taylor4"))) {
+            if (p->phi_normal >= 100.0f && (prefilter || !(variant && !strcmp(variant, "taylor4")))) {
                 // three-term economised series (svgf_device.cuh, economised_series3): one Horner step fewer per tap,
                 // weight error <= 0.56 / (phiN log2e)^3 <= 1.9e-7 absolute
                 const NormalTerm e3 = economised_series3(p->phi_normal);

@@ -214,7 +214,9 @@ __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[R], const PkCentre (&C)[R
     }
 }
 
-template <bool F32, int STEP, int TERMS, int R = kPkRows>
+// PREF: the centre variance comes from the pre-blurred plane a.var_blur (SVGF_VARIANCE_PREFILTER_GAUSS3); a template
+// parameter because even a never-taken branch here costs the register-capped default kernel 4 %
+template <bool F32, int STEP, int TERMS, int R = kPkRows, bool PREF = false>
 __global__ void __launch_bounds__(kPkPairs * (PackedGeom<STEP>::tile_rows / R), 2)
 atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, const float *__restrict__ guide_dz,
                      const typename ColourPlane<F32>::texel *__restrict__ in, typename ColourPlane<F32>::texel *__restrict__ out,
@@ -314,7 +316,7 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
         live1[j] = inside && (g0.y != kBackgroundZ);
         any_live |= live0[j] | live1[j];
         float2 var = make_float2(c1.z, c1.w);                                       // :547 / the pre-blurred plane (GAUSS3)
-        if (a.var_blur && inside) var = __ldg(reinterpret_cast<const float2 *>(a.var_blur + (size_t)gy * a.W + gx));
+        if (PREF && inside) var = __ldg(reinterpret_cast<const float2 *>(a.var_blur + (size_t)gy * a.W + gx));
         C[j].kL = make_float2(a.kL_scale * rsqrtf(1e-10f + var.x), a.kL_scale * rsqrtf(1e-10f + var.y));   // :562
         float2 dz = make_float2(0.f, 0.f);
         if (inside) dz = __ldg(reinterpret_cast<const float2 *>(guide_dz + (size_t)gy * a.W + gx));

@@ -4,12 +4,12 @@
 
 namespace svgf {
 namespace {
-template <bool F32, int STEP, int TERMS, int R>
+template <bool F32, int STEP, int TERMS, int R, bool PREF>
 svgf_status launch_atrous_packed(svgf_ctx *c, AtrousTiledArgs a, int guide_slot, const void *in, void *out, void *hist_colour,
                                  cudaStream_t s) {
     using CT = typename ColourPlane<F32>::texel;
     using G = PackedGeom<STEP>;
-    auto kern = atrous_packed_kernel<F32, STEP, TERMS, R>;
+    auto kern = atrous_packed_kernel<F32, STEP, TERMS, R, PREF>;
     static bool configured[16] = {};
     if (!configured[c->device & 15]) {
         SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
@@ -22,15 +22,15 @@ svgf_status launch_atrous_packed(svgf_ctx *c, AtrousTiledArgs a, int guide_slot,
     SVGF_CUDA(c, cudaGetLastError());
     return SVGF_OK;
 }
-template <bool F32, int TERMS, int R>
+template <bool F32, int TERMS, int R, bool PREF = false>
 svgf_status dispatch_atrous_packed(svgf_ctx *c, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out,
                                    void *hist_colour, cudaStream_t s) {
     switch (a.level) {
-        case 0: return launch_atrous_packed<F32, 1, TERMS, R>(c, a, guide_slot, in, out, hist_colour, s);
-        case 1: return launch_atrous_packed<F32, 2, TERMS, R>(c, a, guide_slot, in, out, hist_colour, s);
-        case 2: return launch_atrous_packed<F32, 4, TERMS, R>(c, a, guide_slot, in, out, hist_colour, s);
-        case 3: return launch_atrous_packed<F32, 8, TERMS, R>(c, a, guide_slot, in, out, hist_colour, s);
-        case 4: return launch_atrous_packed<F32, 16, TERMS, R>(c, a, guide_slot, in, out, hist_colour, s);
+        case 0: return launch_atrous_packed<F32, 1, TERMS, R, PREF>(c, a, guide_slot, in, out, hist_colour, s);
+        case 1: return launch_atrous_packed<F32, 2, TERMS, R, PREF>(c, a, guide_slot, in, out, hist_colour, s);
+        case 2: return launch_atrous_packed<F32, 4, TERMS, R, PREF>(c, a, guide_slot, in, out, hist_colour, s);
+        case 3: return launch_atrous_packed<F32, 8, TERMS, R, PREF>(c, a, guide_slot, in, out, hist_colour, s);
+        case 4: return launch_atrous_packed<F32, 16, TERMS, R, PREF>(c, a, guide_slot, in, out, hist_colour, s);
     }
     return SVGF_UNSUPPORTED;
 }
@@ -43,6 +43,8 @@ svgf_status atrous_packed_f32(svgf_ctx *c, int terms, int rows, const AtrousTile
     // 0.926 / 1.234 ms per 4K frame of a-trous against 0.761 ms for rows = 3 - fewer resident warps cost more than the
     // shared-memory traffic they save; instantiate dispatch_atrous_packed<.., 3, 4> here to repeat it
     if (rows != kPkRows) return SVGF_UNSUPPORTED;
+    if (a.var_blur)   // variance prefilter: instantiated for the three-term series (phi_normal >= 100) only
+        return terms == 3 ? dispatch_atrous_packed<true, 3, kPkRows, true>(c, a, guide_slot, in, out, hist_colour, s) : SVGF_UNSUPPORTED;
     switch (terms) {
         case 3: return dispatch_atrous_packed<true, 3, kPkRows>(c, a, guide_slot, in, out, hist_colour, s);
         case 4: return dispatch_atrous_packed<true, 4, kPkRows>(c, a, guide_slot, in, out, hist_colour, s);
