@@ -226,16 +226,29 @@ variance_7x7(const SpatialArgs &a, const Guide &guide, const typename ColourPlan
     const float kL = kLog2e / a.phi_colour;                                    // :460
     const float phiZ0 = fmaxf(__ldg(guide.dz + i), 1e-8f) * 3.0f * a.phi_depth;  // :461
     float sw = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sm1 = 0.f, sm2 = 0.f;
+    // One window row at a time: the 21 loads of a row are issued together (clamped addresses, so they are unconditional)
+    // and only then consumed.  In steady state this pass is a single wave of a few ten thousand threads and nothing but
+    // load latency: 49 dependent round trips cost 37 us per frame at any resolution, 7 cost a fifth of that.  The taps are
+    // still accumulated in the reference's order (rows, then columns), so the result is bit-identical to the serial loop.
     for (int yy = -3; yy <= 3; yy++) {
         const int py = y + yy;
         if (py < 0 || py >= a.H) continue;
-        for (int xx = -3; xx <= 3; xx++) {
-            const int px = x + xx;
-            if (px < 0 || px >= a.W) continue;                                 // :473
+        typename ColourPlane<F32>::texel rc[7];
+        typename MomentsPlane<F32>::texel rm[7];
+        float4 rg[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const int px = min(max(x + k - 3, 0), a.W - 1);
             const size_t qi = (size_t)py * a.W + px;
-            const float4 cq = ColourPlane<F32>::decode(__ldg(in + qi));
-            const float2 mq = MomentsPlane<F32>::decode(__ldg(mom + qi));
-            const float4 gq = __ldg(guide.n + qi);
+            rc[k] = __ldg(in + qi); rm[k] = __ldg(mom + qi); rg[k] = __ldg(guide.n + qi);
+        }
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const int xx = k - 3, px = x + xx;
+            if (px < 0 || px >= a.W) continue;                                 // :473
+            const float4 cq = ColourPlane<F32>::decode(rc[k]);
+            const float2 mq = MomentsPlane<F32>::decode(rm[k]);
+            const float4 gq = rg[k];
             const float lq = luminance(cq.x, cq.y, cq.z);
             const float phiZ = phiZ0 * sqrtf((float)(xx * xx + yy * yy));      // :488
             const float kZ = (phiZ == 0.0f) ? 0.0f : kLog2e / phiZ;            // :420
