@@ -140,6 +140,18 @@ def max_over_ranks(x, world):
     return float(t.item())
 
 
+def all_ranks(x, world):
+    """x of every rank, in rank order (diagnostics: load balance of the band partition)."""
+    if world == 1:
+        return [x]
+    import torch
+    import torch.distributed as dist
+    t = torch.zeros(world, dtype=torch.float64, device="cuda")
+    t[dist.get_rank()] = x
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t.tolist()]
+
+
 def sum_over_ranks(x, world):
     if world == 1:
         return x
@@ -307,12 +319,22 @@ def run_bands(args, rank, world, local):
     per-level halo rows exchanged between neighbouring ranks (NCCL send/recv over NVLink); strong scaling."""
     import torch
     from svgf_b200 import synth
-    from svgf_b200.bands import balanced_bounds, make_gpu_banded_filter
+    from svgf_b200.bands import balanced_bounds, make_gpu_banded_filter, required_apron
     from svgf_b200.filter import GBuffer
     W, H = WORKLOADS[args.workload]
     dev = torch.device("cuda", local)
     K, Wm = args.steps, args.warmup
     R = K + Wm
+    # auto (-1): when the bands are tall, let a wide apron absorb every level's halo (one overlapped state exchange per
+    # frame, no per-level exchange: the exchanges are latency- and host-bound, redundant rows are cheap); short bands keep
+    # the 32-row apron and exchange before levels 3 and 4
+    if args.band_exchange_from < 0:
+        wide = required_apron(args.levels, args.levels, args.band_max_motion)
+        wide = (wide + 7) // 8 * 8
+        if H // world >= 4 * wide:
+            args.band_exchange_from, args.band_apron = args.levels, max(args.band_apron, wide)
+        else:
+            args.band_exchange_from = min(3, args.levels)
     L = min(args.band_exchange_from, args.levels)
     cdt = torch.float16 if args.storage == "f16" else torch.float32
     # every rank generates the full frames procedurally on its own GPU and keeps only its local rows (band + aprons)
@@ -326,6 +348,9 @@ def run_bands(args, rank, world, local):
     bf = make_gpu_banded_filter(W, H, rank, world, dev, storage=args.storage, levels=args.levels, apron=args.band_apron,
                                 exchange_from_level=L, max_motion_rows=args.band_max_motion, overlap_state=bool(args.band_overlap_state),
                                 bounds=bounds)
+    if args.band_dry_run:
+        import svgf_b200.bands as _bands
+        _bands.post_exchange = lambda *a_, **k_: []
     f, band = bf.f, bf.band
     Hl = band.local_height
     ring_g = [GBuffer(W, Hl, dev) for _ in range(R)]
@@ -361,7 +386,11 @@ def run_bands(args, rank, world, local):
     barrier(world)
     sampler.stop_flag = True
     ms_max = max_over_ranks(e0.elapsed_time(e1), world)
+    # per-rank time: with --band-dry-run (no exchanges, wrong pixels) the ranks are independent and this is each band's own
+    # compute + host cost, i.e. the load balance; otherwise neighbours wait for each other and the values converge
+    ms_by_rank = all_ranks(e0.elapsed_time(e1) / K, world)
     launches = sum_over_ranks(f.launches - launches0, world)
+    all_rows = [int(v) for v in all_ranks(float(Hl), world)]
     sampler.join()
     if rank != 0:
         return None
@@ -379,7 +408,8 @@ def run_bands(args, rank, world, local):
                                f"a-trous levels, halo exchange (NCCL send/recv) before levels >= {L}, state exchange "
                                f"{'overlapped with levels 1..' if args.band_overlap_state else 'at frame start'}", "width": W, "height": H,
                    "atrous_levels": args.levels, "storage": args.storage, "band_rows": band.y1 - band.y0, "apron_rows": bf.apron,
-                   "band_bounds": bounds, "exchange_from_level": L, "overlap_state": bool(args.band_overlap_state), "exchanges_per_frame": 1 + args.levels - L,
+                   "band_bounds": bounds, "exchange_from_level": L, "overlap_state": bool(args.band_overlap_state), "exchanges_per_frame": 1 + args.levels - L, "local_rows_by_rank": all_rows,
+                   "ms_per_step_by_rank": [round(v, 4) for v in ms_by_rank], "dry_run_no_exchange": bool(args.band_dry_run),
                    "halo_bytes_per_frame_all_ranks": int(halo_bytes),
                    "l2": "every step reads a fresh frame"},
         "gpu_launches": int(launches),
@@ -516,10 +546,11 @@ def main():
     ap.add_argument("--prefilter", type=int, default=0, help="svgf_params.variance_prefilter (1 = 3x3 Gaussian, not in the reference)")
     ap.add_argument("--reproj", type=int, default=0, help="svgf_params.reproj_mode (1 = bilinear 2x2, not in the reference)")
     ap.add_argument("--flags", type=int, default=0, help="svgf_params.flags for A/B runs (8 = no uniform-normal tile shortcut)")
+    ap.add_argument("--band-dry-run", type=int, default=0, help="--mode bands diagnostics: 1 = skip every exchange (pixels near band edges are wrong); shows per-rank load")
     ap.add_argument("--band-balance", type=int, default=1, help="--mode bands: 1 = band heights balanced by estimated work (background rows are cheap), 0 = equal heights")
-    ap.add_argument("--band-bg-cost", type=float, default=0.2, help="--mode bands: cost of a background pixel relative to a filtered one")
+    ap.add_argument("--band-bg-cost", type=float, default=0.45, help="--mode bands: cost of a background pixel relative to a filtered one")
     ap.add_argument("--band-apron", type=int, default=32, help="--mode bands: apron rows on each side of a band")
-    ap.add_argument("--band-exchange-from", type=int, default=3, help="--mode bands: first a-trous level that exchanges its halo (lower levels recompute it in the apron)")
+    ap.add_argument("--band-exchange-from", type=int, default=-1, help="--mode bands: first a-trous level that exchanges its halo (lower levels recompute it in the apron); -1 = choose from the band height")
     ap.add_argument("--band-max-motion", type=int, default=8, help="--mode bands: vertical reach (rows) of the temporal gather covered by the apron")
     ap.add_argument("--band-overlap-state", type=int, default=1, help="--mode bands: 1 = post the previous-frame state exchange under levels 1..N-1")
     ap.add_argument("--mode", default="streams", choices=["streams", "bands"],

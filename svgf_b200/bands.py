@@ -69,7 +69,7 @@ def balanced_bounds(row_cost, world, min_rows=APRON):
     The a-trous levels skip background pixels (reference src/Filter.cuh:554-558) and take a cheaper path on uniform
     tiles, so rows cost very different amounts; with equal-height bands the slowest rank sets the frame time.  row_cost
     is any per-row estimate every rank can compute identically (bench.py: fraction of non-background pixels of the
-    first frame, background weighted 0.2).  Every band keeps at least `min_rows` rows (it must be able to feed its
+    first frame, background weighted 0.45 - measured with `bench.py --band-dry-run 1` on 8 B200s).  Every band keeps at least `min_rows` rows (it must be able to feed its
     neighbours' aprons)."""
     import numpy as np
     c = np.maximum(np.asarray(row_cost, dtype=np.float64), 0.0) + 1e-9
