@@ -136,6 +136,26 @@ __device__ __forceinline__ void pk_tap1(float &S, float &Ar, float &Ag, float &A
     Av = fmaf(w * w, qv, Av);
 }
 
+// Colour planes of the tile.  HC = false: two float4 planes {r0,r1,g0,g1} {b0,b1,v0,v1}.  HC = true (fp16 storage only):
+// ONE uint4 plane of half2 pairs {r0r1, g0g1, b0b1, v0v1} - the clamped values are fp16 numbers, so the narrowing is
+// exact and every result stays bit-identical, while a tap reads 16 instead of 32 bytes of colour (the level sits on the
+// shared-memory pipe: L1TEX 79-87 %, profiles/atrous_r01s8.*); the price is 8 half->float conversions per tap row.
+__device__ __forceinline__ float2 pk_h2f(unsigned int h) { return __half22float2(*reinterpret_cast<const __half2 *>(&h)); }
+__device__ __forceinline__ unsigned int pk_f2h(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const unsigned int *>(&h);
+}
+template <bool HC>
+__device__ __forceinline__ void pk_load_colour(const float4 *sC0, const float4 *sC1, int si, float2 &r, float2 &g, float2 &b, float2 &v) {
+    if (HC) {
+        const uint4 t = reinterpret_cast<const uint4 *>(sC0)[si];
+        r = pk_h2f(t.x); g = pk_h2f(t.y); b = pk_h2f(t.z); v = pk_h2f(t.w);
+    } else {
+        const float4 c0 = sC0[si], c1 = sC1[si];
+        r = make_float2(c0.x, c0.y); g = make_float2(c0.z, c0.w); b = make_float2(c1.x, c1.y); v = make_float2(c1.z, c1.w);
+    }
+}
+
 __device__ __forceinline__ constexpr float tap_inv_len(int ax, int ay) {
     const int l2 = ax * ax + ay * ay;   // 1 2 4 5 8
     return l2 == 1 ? 1.0f : l2 == 2 ? 0.70710678f : l2 == 4 ? 0.5f : l2 == 5 ? 0.44721360f : 0.35355339f;
@@ -146,7 +166,7 @@ __device__ __forceinline__ constexpr float tap_inv_len(int ax, int ay) {
 // single-level kernel; the fused two-level kernel passes its staging pitch, doubled for the dilated level)
 // R = outputs per thread and column: a staged tap row serves up to min(R, 5) of them, so shared-memory traffic per
 // output falls as (R + 4) / R while the per-thread state grows by 24 registers per row.
-template <int STEP, int TERMS, bool UNIF, int PITCH = PackedGeom<STEP>::pairs, int R = kPkRows>
+template <int STEP, int TERMS, bool UNIF, int PITCH = PackedGeom<STEP>::pairs, int R = kPkRows, bool HC = false>
 __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[R], const PkCentre (&C)[R], const float4 *sC0, const float4 *sC1,
                                             const float4 *sG0, const float4 *sG1, const float2 *sL, int row0, int pcol,
                                             const PkCoef &k, float un, float pn) {
@@ -157,12 +177,11 @@ __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[R], const PkCentre (&C)[R
 #pragma unroll
             for (int t = -2; t < R + 2; t++) {
                 const int si = (row0 + t) * G::pairs + pcol + dx * (STEP / 2);
-                const float4 c0 = sC0[si], c1 = sC1[si];
                 float4 g0, g1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (UNIF) { const float2 zz = *reinterpret_cast<const float2 *>(&sG0[si]); g0 = make_float4(zz.x, zz.y, 0.f, 0.f); }
                 else { g0 = sG0[si]; g1 = sG1[si]; }
                 PkTap q;
-                q.r = make_float2(c0.x, c0.y); q.g = make_float2(c0.z, c0.w); q.b = make_float2(c1.x, c1.y); q.v = make_float2(c1.z, c1.w);
+                pk_load_colour<HC>(sC0, sC1, si, q.r, q.g, q.b, q.v);
                 q.z = make_float2(g0.x, g0.y); q.nx = make_float2(g0.z, g0.w); q.ny = make_float2(g1.x, g1.y); q.nz = make_float2(g1.z, g1.w);
                 q.l = sL[si];
 #pragma unroll
@@ -184,12 +203,11 @@ __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[R], const PkCentre (&C)[R
 #pragma unroll
             for (int m = -1; m <= 1; m++) {
                 const int si = (row0 + t) * G::pairs + pcol + m;
-                const float4 c0 = sC0[si], c1 = sC1[si];
                 float4 g0, g1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (UNIF) { const float2 zz = *reinterpret_cast<const float2 *>(&sG0[si]); g0 = make_float4(zz.x, zz.y, 0.f, 0.f); }
                 else { g0 = sG0[si]; g1 = sG1[si]; }
                 PkTap q;
-                q.r = make_float2(c0.x, c0.y); q.g = make_float2(c0.z, c0.w); q.b = make_float2(c1.x, c1.y); q.v = make_float2(c1.z, c1.w);
+                pk_load_colour<HC>(sC0, sC1, si, q.r, q.g, q.b, q.v);
                 q.z = make_float2(g0.x, g0.y); q.nx = make_float2(g0.z, g0.w); q.ny = make_float2(g1.x, g1.y); q.nz = make_float2(g1.z, g1.w);
                 q.l = sL[si];
 #pragma unroll
@@ -216,7 +234,7 @@ __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[R], const PkCentre (&C)[R
 
 // PREF: the centre variance comes from the pre-blurred plane a.var_blur (SVGF_VARIANCE_PREFILTER_GAUSS3); a template
 // parameter because even a never-taken branch here costs the register-capped default kernel 4 %
-template <bool F32, int STEP, int TERMS, int R = kPkRows, bool PREF = false>
+template <bool F32, int STEP, int TERMS, int R = kPkRows, bool PREF = false, bool HC = false>
 __global__ void __launch_bounds__(kPkPairs * (PackedGeom<STEP>::tile_rows / R), 2)
 atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, const float *__restrict__ guide_dz,
                      const typename ColourPlane<F32>::texel *__restrict__ in, typename ColourPlane<F32>::texel *__restrict__ out,
@@ -224,6 +242,7 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     using G = PackedGeom<STEP>;
     constexpr int kThreads = kPkPairs * (G::tile_rows / R);   // R = 3: 256 threads, R = 4: 192
     static_assert(G::tile_rows % R == 0, "row groups must tile the 12 rows");
+    static_assert(!(HC && F32), "half-precision colour tiles are exact for fp16 storage only");
     using CT = typename ColourPlane<F32>::texel;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sC0 = reinterpret_cast<float4 *>(smem_raw);        // r0 r1 g0 g1
@@ -278,8 +297,12 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
             const float4 c0 = ColourPlane<F32>::decode(rc0[i]), c1 = ColourPlane<F32>::decode(rc1[i]);
             const float r0 = __saturatef(c0.x), g0 = __saturatef(c0.y), b0 = __saturatef(c0.z), v0 = __saturatef(c0.w);   // :543,:586
             const float r1 = __saturatef(c1.x), g1 = __saturatef(c1.y), b1 = __saturatef(c1.z), v1 = __saturatef(c1.w);
-            sC0[idx] = make_float4(r0, r1, g0, g1);
-            sC1[idx] = make_float4(b0, b1, v0, v1);
+            if (HC) {
+                reinterpret_cast<uint4 *>(sC0)[idx] = make_uint4(pk_f2h(r0, r1), pk_f2h(g0, g1), pk_f2h(b0, b1), pk_f2h(v0, v1));
+            } else {
+                sC0[idx] = make_float4(r0, r1, g0, g1);
+                sC1[idx] = make_float4(b0, b1, v0, v1);
+            }
             sG0[idx] = make_float4(rg0[i].x, rg1[i].x, rg0[i].y, rg1[i].y);
             sG1[idx] = make_float4(rg0[i].z, rg1[i].z, rg0[i].w, rg1[i].w);
             sL[idx] = make_float2(luminance(r0, g0, b0), luminance(r1, g1, b1));
@@ -303,11 +326,10 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
 #pragma unroll
     for (int j = 0; j < R; j++) {
         const int si = (row0 + j) * G::pairs + pcol;
-        const float4 c0 = sC0[si], c1 = sC1[si], g0 = sG0[si], g1 = sG1[si];
+        const float4 g0 = sG0[si], g1 = sG1[si];
         const int gy = y0 + (tg * R + j) * STEP;
         A[j].S = f2bc(1.0f);                                                       // :567-568
-        A[j].r = make_float2(c0.x, c0.y); A[j].g = make_float2(c0.z, c0.w);
-        A[j].b = make_float2(c1.x, c1.y); A[j].v = make_float2(c1.z, c1.w);
+        pk_load_colour<HC>(sC0, sC1, si, A[j].r, A[j].g, A[j].b, A[j].v);
         C[j].lc = sL[si];
         C[j].zc = make_float2(g0.x, g0.y); C[j].nx = make_float2(g0.z, g0.w);
         C[j].ny = make_float2(g1.x, g1.y); C[j].nz = make_float2(g1.z, g1.w);
@@ -315,7 +337,7 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
         live0[j] = inside && (g0.x != kBackgroundZ);                               // :554: background passes through
         live1[j] = inside && (g0.y != kBackgroundZ);
         any_live |= live0[j] | live1[j];
-        float2 var = make_float2(c1.z, c1.w);                                       // :547 / the pre-blurred plane (GAUSS3)
+        float2 var = A[j].v;                                                        // :547 / the pre-blurred plane (GAUSS3)
         if (PREF && inside) var = __ldg(reinterpret_cast<const float2 *>(a.var_blur + (size_t)gy * a.W + gx));
         C[j].kL = make_float2(a.kL_scale * rsqrtf(1e-10f + var.x), a.kL_scale * rsqrtf(1e-10f + var.y));   // :562
         float2 dz = make_float2(0.f, 0.f);
@@ -324,8 +346,8 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     }
 
     if (__any_sync(0xffffffffu, any_live)) {
-        if (uniform_n) pk_all_taps<STEP, TERMS, true, G::pairs, R>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, un, pn);
-        else pk_all_taps<STEP, TERMS, false, G::pairs, R>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, 0.f, 0.f);
+        if (uniform_n) pk_all_taps<STEP, TERMS, true, G::pairs, R, HC>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, un, pn);
+        else pk_all_taps<STEP, TERMS, false, G::pairs, R, HC>(A, C, sC0, sC1, sG0, sG1, sL, row0, pcol, k, 0.f, 0.f);
     }
 
     // ---- normalise and store both pixels of the pair (:615-622) ----
@@ -335,12 +357,13 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
         if (gx >= a.W || gy >= a.H) continue;
         const size_t gi = (size_t)gy * a.W + gx;
         const int si = (row0 + j) * G::pairs + pcol;
-        const float4 c0 = sC0[si], c1 = sC1[si];
+        float2 cr, cg, cb, cv;
+        pk_load_colour<HC>(sC0, sC1, si, cr, cg, cb, cv);
         const float i0 = __frcp_rn(A[j].S.x), i1 = __frcp_rn(A[j].S.y);
         float4 o0 = make_float4(A[j].r.x * i0, A[j].g.x * i0, A[j].b.x * i0, A[j].v.x * (i0 * i0));
         float4 o1 = make_float4(A[j].r.y * i1, A[j].g.y * i1, A[j].b.y * i1, A[j].v.y * (i1 * i1));
-        if (!live0[j]) o0 = make_float4(c0.x, c0.z, c1.x, c1.z);                     // :556 (clamped centre)
-        if (!live1[j]) o1 = make_float4(c0.y, c0.w, c1.y, c1.w);
+        if (!live0[j]) o0 = make_float4(cr.x, cg.x, cb.x, cv.x);                     // :556 (clamped centre)
+        if (!live1[j]) o1 = make_float4(cr.y, cg.y, cb.y, cv.y);
         const CT e0 = ColourPlane<F32>::encode(o0), e1 = ColourPlane<F32>::encode(o1);
         const bool h0 = (a.level == 0) && hist_colour && live0[j], h1 = (a.level == 0) && hist_colour && live1[j];
         if (F32) {

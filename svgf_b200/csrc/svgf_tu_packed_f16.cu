@@ -4,12 +4,12 @@
 
 namespace svgf {
 namespace {
-template <bool F32, int STEP, int TERMS, int R, bool PREF>
+template <bool F32, int STEP, int TERMS, int R, bool PREF, bool HC>
 svgf_status launch_atrous_packed(svgf_ctx *c, AtrousTiledArgs a, int guide_slot, const void *in, void *out, void *hist_colour,
                                  cudaStream_t s) {
     using CT = typename ColourPlane<F32>::texel;
     using G = PackedGeom<STEP>;
-    auto kern = atrous_packed_kernel<F32, STEP, TERMS, R, PREF>;
+    auto kern = atrous_packed_kernel<F32, STEP, TERMS, R, PREF, HC>;
     static bool configured[16] = {};
     if (!configured[c->device & 15]) {
         SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
@@ -22,15 +22,15 @@ svgf_status launch_atrous_packed(svgf_ctx *c, AtrousTiledArgs a, int guide_slot,
     SVGF_CUDA(c, cudaGetLastError());
     return SVGF_OK;
 }
-template <bool F32, int TERMS, int R, bool PREF = false>
+template <bool F32, int TERMS, int R, bool PREF = false, bool HC = false>
 svgf_status dispatch_atrous_packed(svgf_ctx *c, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out,
                                    void *hist_colour, cudaStream_t s) {
     switch (a.level) {
-        case 0: return launch_atrous_packed<F32, 1, TERMS, R, PREF>(c, a, guide_slot, in, out, hist_colour, s);
-        case 1: return launch_atrous_packed<F32, 2, TERMS, R, PREF>(c, a, guide_slot, in, out, hist_colour, s);
-        case 2: return launch_atrous_packed<F32, 4, TERMS, R, PREF>(c, a, guide_slot, in, out, hist_colour, s);
-        case 3: return launch_atrous_packed<F32, 8, TERMS, R, PREF>(c, a, guide_slot, in, out, hist_colour, s);
-        case 4: return launch_atrous_packed<F32, 16, TERMS, R, PREF>(c, a, guide_slot, in, out, hist_colour, s);
+        case 0: return launch_atrous_packed<F32, 1, TERMS, R, PREF, HC>(c, a, guide_slot, in, out, hist_colour, s);
+        case 1: return launch_atrous_packed<F32, 2, TERMS, R, PREF, HC>(c, a, guide_slot, in, out, hist_colour, s);
+        case 2: return launch_atrous_packed<F32, 4, TERMS, R, PREF, HC>(c, a, guide_slot, in, out, hist_colour, s);
+        case 3: return launch_atrous_packed<F32, 8, TERMS, R, PREF, HC>(c, a, guide_slot, in, out, hist_colour, s);
+        case 4: return launch_atrous_packed<F32, 16, TERMS, R, PREF, HC>(c, a, guide_slot, in, out, hist_colour, s);
     }
     return SVGF_UNSUPPORTED;
 }
@@ -42,6 +42,9 @@ svgf_status atrous_packed_f16(svgf_ctx *c, int terms, int rows, const AtrousTile
     // rows = 4 (192 threads, 164 registers) and rows = 6 (128 threads, 238 registers) were measured on B200 and lost:
     // 0.926 / 1.234 ms per 4K frame of a-trous against 0.761 ms for rows = 3 - fewer resident warps cost more than the
     // shared-memory traffic they save; instantiate dispatch_atrous_packed<.., 3, 4> here to repeat it
+    // the half-precision colour tile (template parameter HC of the kernel: 16 instead of 32 bytes of colour per tap, 8
+    // conversions per tap row) was measured on B200 and lost: 0.825 against 0.753 ms per 4K frame of a-trous; instantiate
+    // dispatch_atrous_packed<false, 3, kPkRows, false, true> here to repeat it
     if (rows != kPkRows) return SVGF_UNSUPPORTED;
     if (a.var_blur)   // variance prefilter: instantiated for the three-term series (phi_normal >= 100) only
         return terms == 3 ? dispatch_atrous_packed<false, 3, kPkRows, true>(c, a, guide_slot, in, out, hist_colour, s) : SVGF_UNSUPPORTED;

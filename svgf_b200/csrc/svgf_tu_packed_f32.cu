@@ -4,7 +4,7 @@
 
 namespace svgf {
 namespace {
-template <bool F32, int STEP, int TERMS, int R, bool PREF>
+template <bool F32, int STEP, int TERMS, int R, bool PREF, bool HC = false>
 svgf_status launch_atrous_packed(svgf_ctx *c, AtrousTiledArgs a, int guide_slot, const void *in, void *out, void *hist_colour,
                                  cudaStream_t s) {
     using CT = typename ColourPlane<F32>::texel;
