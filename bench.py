@@ -458,7 +458,8 @@ def run_reference(args, rank, world, local):
     import numpy as np
     from oracle_lib import RefKernels, RefParams, ref, ref_available
     from svgf_b200 import _lib as L
-    base = {"impl": "reference", "metric": "svgf_frame_throughput", "unit": "Gpix/s", "n_gpus": 1, "steps": args.steps,
+    # n_gpus is the launch's N (the contract's key); the reference has no multi-GPU path, so one GPU does the work
+    base = {"impl": "reference", "metric": "svgf_frame_throughput", "unit": "Gpix/s", "n_gpus": max(1, world), "gpus_used": 1, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
             "config": {"workload": f"BASELINE configs[2]: {W}x{H} camera-pan sequence, temporal + variance + {args.levels} a-trous levels",
                        "width": W, "height": H, "atrous_levels": args.levels, "storage": "f16"}}
