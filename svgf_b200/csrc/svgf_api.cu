@@ -207,7 +207,7 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
     if (prefilter) {
         // blurred variance of this level's input, read by the level kernel for the centre pixel only
         if (!c->var_blur) SVGF_CUDA(c, cudaMalloc(&c->var_blur, (size_t)c->W * c->H * sizeof(float)));
-        const dim3 g((c->W + 29) / 30, (c->H + 7) / 8);
+        const dim3 g((c->W + 29) / 30, (c->H + 8 * kGauss3Rows - 1) / (8 * kGauss3Rows));
         variance_gauss3_kernel<F32><<<g, 256, 0, s>>>(c->W, c->H, (const CT *)in, c->var_blur);
         c->launches++;
         SVGF_CUDA(c, cudaGetLastError());

@@ -191,20 +191,33 @@ struct SpatialArgs {
 // (1 2 1; 2 4 2; 1 2 1) / 16, coordinates clamped to the image.  One warp produces 30 pixels of one row: every lane
 // combines rows y-1, y, y+1 of its own column (lanes 0 and 31 carry the neighbour columns), the horizontal pass is two
 // warp shuffles.  The weights are powers of two, so the only roundings are the four additions, in the oracle's order.
+constexpr int kGauss3Rows = 4;   // output rows per thread: 6 loaded rows serve 4 outputs
 template <bool F32>
 __global__ void __launch_bounds__(256)
 variance_gauss3_kernel(int W, int H, const typename ColourPlane<F32>::texel *__restrict__ in, float *__restrict__ out) {
     const int lane = threadIdx.x & 31;
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (y >= H) return;                                   // uniform per warp
+    const int y0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * kGauss3Rows;
+    if (y0 >= H) return;                                  // uniform per warp
     const int x = blockIdx.x * 30 + lane - 1;
-    const int px = min(max(x, 0), W - 1), ym = max(y - 1, 0), yp = min(y + 1, H - 1);
-    const float a = clamp01(ColourPlane<F32>::decode(__ldg(in + (size_t)ym * W + px)).w);
-    const float b = clamp01(ColourPlane<F32>::decode(__ldg(in + (size_t)y * W + px)).w);
-    const float c = clamp01(ColourPlane<F32>::decode(__ldg(in + (size_t)yp * W + px)).w);
-    const float col = __fadd_rn(__fadd_rn(0.25f * a, 0.5f * b), 0.25f * c);
-    const float l = __shfl_up_sync(0xffffffffu, col, 1), r = __shfl_down_sync(0xffffffffu, col, 1);
-    if (lane >= 1 && lane <= 30 && x < W) out[(size_t)y * W + x] = __fadd_rn(__fadd_rn(0.25f * l, 0.5f * col), 0.25f * r);
+    const int px = min(max(x, 0), W - 1);
+    // only the variance channel of a texel is read: 2 bytes at offset 6 (fp16 storage) / 4 bytes at offset 12 (fp32)
+    float v[kGauss3Rows + 2];
+#pragma unroll
+    for (int r = 0; r < kGauss3Rows + 2; r++) {
+        const int py = min(max(y0 + r - 1, 0), H - 1);
+        const size_t qi = (size_t)py * W + px;
+        float raw;
+        if (F32) raw = __ldg(reinterpret_cast<const float *>(in) + 4 * qi + 3);
+        else raw = __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short *>(in) + 4 * qi + 3)));
+        v[r] = clamp01(raw);
+    }
+#pragma unroll
+    for (int r = 0; r < kGauss3Rows; r++) {
+        const int y = y0 + r;
+        const float col = __fadd_rn(__fadd_rn(0.25f * v[r], 0.5f * v[r + 1]), 0.25f * v[r + 2]);
+        const float l = __shfl_up_sync(0xffffffffu, col, 1), rr = __shfl_down_sync(0xffffffffu, col, 1);
+        if (lane >= 1 && lane <= 30 && x < W && y < H) out[(size_t)y * W + x] = __fadd_rn(__fadd_rn(0.25f * l, 0.5f * col), 0.25f * rr);
+    }
 }
 
 // ---- variance estimation: reference filter::FilterMoments (src/Filter.cuh:430-525) -------------------------
