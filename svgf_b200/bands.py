@@ -111,25 +111,38 @@ def check_band(band, apron):
         raise ValueError(f"band of {band.y1 - band.y0} rows is shorter than the {apron}-row halo")
 
 
-def post_exchange(band, planes, rows, group=None):
-    """Start the exchange of `rows` apron rows on each side of the band for every tensor of `planes` and return the
-    pending work handles ([] on one rank); finish_exchange() completes it.  One batched send/recv."""
-    if band.world == 1 or rows <= 0:
-        return []
-    ops, keep = [], []
+def build_exchange_ops(band, planes, rows, group=None):
+    """The batched send/recv list that refreshes `rows` apron rows on each side of the band for every tensor of `planes`
+    (local images, dim 0 = rows) with the neighbours' band rows.  The list only refers to tensor views, so it can be built
+    once per (planes, rows) and posted every frame."""
+    ops = []
     up, down = band.rank - 1, band.rank + 1
     for t in planes:
         if up >= 0:
             send = t[band.loc(band.y0):band.loc(band.y0 + rows)]              # my top band rows -> upper neighbour's bottom apron
             recv = t[band.loc(band.y0 - rows):band.loc(band.y0)]              # upper neighbour's bottom band rows -> my top apron
             ops += [dist.P2POp(dist.isend, send, up, group), dist.P2POp(dist.irecv, recv, up, group)]
-            keep += [send, recv]
         if down < band.world:
             send = t[band.loc(band.y1 - rows):band.loc(band.y1)]
             recv = t[band.loc(band.y1):band.loc(band.y1 + rows)]
             ops += [dist.P2POp(dist.isend, send, down, group), dist.P2POp(dist.irecv, recv, down, group)]
-            keep += [send, recv]
-    return [(w, keep) for w in dist.batch_isend_irecv(ops)]
+    return ops
+
+
+def post_exchange(band, planes, rows, group=None, cache=None):
+    """Start the exchange and return the pending work handles ([] on one rank); finish_exchange() completes it.  One
+    batched send/recv.  `cache` (a dict owned by the caller) keeps the op lists across frames: building 12 tensor views
+    and P2POps per call is host time that a 0.5 ms band frame notices."""
+    if band.world == 1 or rows <= 0:
+        return []
+    if cache is None:
+        ops = build_exchange_ops(band, planes, rows, group)
+    else:
+        key = (tuple(t.data_ptr() for t in planes), rows)
+        ops = cache.get(key)
+        if ops is None:
+            ops = cache[key] = build_exchange_ops(band, planes, rows, group)
+    return [(w, ops) for w in dist.batch_isend_irecv(ops)]
 
 
 def finish_exchange(pending):
@@ -137,10 +150,10 @@ def finish_exchange(pending):
         w.wait()
 
 
-def exchange_rows(band, planes, rows, group=None):
+def exchange_rows(band, planes, rows, group=None, cache=None):
     """Refresh `rows` apron rows on each side of the band in every tensor of `planes` (local images, dim 0 = rows)
     with the neighbours' band rows.  One batched send/recv per call; a no-op on one rank."""
-    finish_exchange(post_exchange(band, planes, rows, group))
+    finish_exchange(post_exchange(band, planes, rows, group, cache))
 
 
 class BandedFilter:
@@ -168,6 +181,7 @@ class BandedFilter:
         self.state_apron = self.apron if state_apron is None else min(state_apron, self.apron)
         self.overlap_state = overlap_state
         self._pending_state = None
+        self._op_cache = {}
         self.frame = 0
 
     def _t(self, buf):
@@ -184,20 +198,31 @@ class BandedFilter:
             finish_exchange(self._pending_state)
             self._pending_state = None
         elif self.frame > 0:                    # previous-frame state in the aprons (the reset frame has none)
-            exchange_rows(b, self._state_planes(Q), self.state_apron, self.group)
+            exchange_rows(b, self._state_planes(Q), self.state_apron, self.group, self._op_cache)
         src = self.ops["temporal_variance"](f)                    # -> FilterBuffer[k] holding the variance pass's output
         k = 0 if src is f.FilterBuffer[0] else 1
-        for level in range(self.levels):
+        level = 0
+        while level < self.levels:
             if level >= self.exchange_from_level:
-                exchange_rows(b, [self._t(f.FilterBuffer[k])], 2 << level, self.group)
-            self.ops["atrous_level"](f, level, f.FilterBuffer[k], f.FilterBuffer[1 - k])
-            k = 1 - k
+                exchange_rows(b, [self._t(f.FilterBuffer[k])], 2 << level, self.group, self._op_cache)
+            # levels that need no exchange in between go out as ONE backend call (fewer host round trips per frame);
+            # the group ends after level 0 when the state exchange is to be posted there
+            n = 1
+            while (level + n < self.levels and level + n < self.exchange_from_level and not (self.overlap_state and level == 0)):
+                n += 1
+            if "atrous_levels" in self.ops:
+                k = self.ops["atrous_levels"](f, level, n, k)
+            else:
+                for lv in range(level, level + n):
+                    self.ops["atrous_level"](f, lv, f.FilterBuffer[k], f.FilterBuffer[1 - k])
+                    k = 1 - k
             if level == 0 and self.overlap_state:
                 # colour history (written by level 0), moments and history lengths of THIS frame are final: they are the
                 # next frame's previous-frame state
-                self._pending_state = post_exchange(b, self._state_planes(P), self.state_apron, self.group)
+                self._pending_state = post_exchange(b, self._state_planes(P), self.state_apron, self.group, self._op_cache)
+            level += n
         if self.levels == 0 and self.overlap_state:
-            self._pending_state = post_exchange(b, self._state_planes(P), self.state_apron, self.group)
+            self._pending_state = post_exchange(b, self._state_planes(P), self.state_apron, self.group, self._op_cache)
         self.result_index = k
         self.frame += 1
         return f.FilterBuffer[k]
@@ -242,7 +267,24 @@ def _gpu_atrous_level(f, level, src, dst):
     assert res.value == dst.data_ptr()
 
 
-GPU_OPS = {"temporal_variance": _gpu_temporal_variance, "atrous_level": _gpu_atrous_level, "as_tensor": lambda t: t}
+def _gpu_atrous_levels(f, first, n, k):
+    """Levels first .. first+n-1 in one svgf_atrous call, ping-ponging FilterBuffer[k] -> FilterBuffer[1-k] -> ...;
+    returns the index of the buffer holding the result."""
+    import ctypes as C
+    from ._lib import SVGF_OK, SvgfError
+    P = f.PingPongInx
+    g = f.Framebuffer[P].as_struct()
+    res = C.c_void_p()
+    src, dst = f.FilterBuffer[k], f.FilterBuffer[1 - k]
+    st = f.lib.svgf_atrous(f._ctx, C.byref(f.params), C.byref(g), C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()),
+                           C.c_void_p(f.RenderBuffer[P].data_ptr()), first, n, C.byref(res), f._stream())
+    if st != SVGF_OK:
+        raise SvgfError(st, "svgf_atrous", f.lib.svgf_last_cuda_error(f._ctx))
+    return 0 if res.value == f.FilterBuffer[0].data_ptr() else 1
+
+
+GPU_OPS = {"temporal_variance": _gpu_temporal_variance, "atrous_level": _gpu_atrous_level, "atrous_levels": _gpu_atrous_levels,
+           "as_tensor": lambda t: t}
 
 
 def make_gpu_banded_filter(W, H, rank, world, device, storage="f16", levels=5, group=None, apron=APRON, exchange_from_level=0,

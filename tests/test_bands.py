@@ -203,3 +203,33 @@ def test_bands_on_gpu_equal_the_whole_frame():
         full.EndFrame()
         for f in parts:
             f.EndFrame()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("from_level,overlap", [(0, False), (3, True), (5, True)])
+def test_banded_driver_on_one_rank_equals_svgf_frame(from_level, overlap):
+    """world = 1: no exchange, but the driver's own call sequence (svgf_frame with zero levels, then the a-trous levels in
+    groups through svgf_atrous) must reproduce one svgf_frame call bit for bit, in every grouping."""
+    from svgf_b200 import SvgfFilter
+    from svgf_b200.bands import make_gpu_banded_filter
+    Wg, Hg = 256, 192
+    full = SvgfFilter(Wg, Hg, storage="f16")
+    full.Reset()
+    bf = make_gpu_banded_filter(Wg, Hg, 0, 1, torch.device("cuda", 0), exchange_from_level=from_level, overlap_state=overlap)
+    bf.f.Reset()
+    for t in range(FRAMES):
+        planes = synth.frame_host(Wg, Hg, t, vert_px=2.5)
+        for f in (full, bf.f):
+            P = f.PingPongInx
+            f.Framebuffer[P].normal.copy_(torch.from_numpy(planes["normal"].view(np.int16)))
+            f.Framebuffer[P].uv.copy_(torch.from_numpy(planes["uv"].view(np.int16)))
+            f.Framebuffer[P].motion.copy_(torch.from_numpy(planes["motion"]))
+            f.RenderBuffer[P].copy_(torch.from_numpy(planes["colour"]))
+        full.Filter()
+        res = bf.Filter()
+        torch.cuda.synchronize()
+        assert torch.equal(res.view(torch.uint8), full.FilterBuffer[0].view(torch.uint8)), f"frame {t}"
+        assert torch.equal(bf.f.HistoryLengthBuffer, full.HistoryLengthBuffer)
+        assert torch.equal(bf.f.RenderBuffer[P].view(torch.uint8), full.RenderBuffer[P].view(torch.uint8))
+        full.EndFrame(); bf.EndFrame()
+    bf.drain()
