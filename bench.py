@@ -31,18 +31,20 @@ OUT_BYTES_PER_PX = {"f16": 8, "f32": 16}
 
 def ncu_traffic_per_launch(args):
     """Mean dram__bytes_read + dram__bytes_write per a-trous launch from the committed `ncu --set full` capture of this
-    command (profiles/atrous_r01s8.metrics.csv, five consecutive levels of one 4K fp16 frame), or None for any other
+    command (profiles/atrous_r01final.metrics.csv, five consecutive levels of one 4K fp16 frame), or None for any other
     workload: the capture is evidence for the default configuration only."""
     import csv
     if args.workload != "4k" or args.storage != "f16" or args.levels != 5 or args.flags or args.prefilter or args.reproj:
         return None, None
-    path = os.path.join(ROOT, "profiles", "atrous_r01s8.metrics.csv")
+    path = os.path.join(ROOT, "profiles", "atrous_r01final.metrics.csv")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "atrous_r01s8.metrics.csv")
     try:
         rows = {r[0]: r for r in csv.reader(open(path)) if r}
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         rd, wr = rows["dram__bytes_read.sum"], rows["dram__bytes_write.sum"]
         per = [float(a) * scale[rd[1]] + float(b) * scale[wr[1]] for a, b in zip(rd[2:], wr[2:])]
-        return int(sum(per) / len(per)), "profiles/atrous_r01s8.metrics.csv (ncu --set full, mean of %d levels)" % len(per)
+        return int(sum(per) / len(per)), "profiles/%s (ncu --set full, mean of %d levels)" % (os.path.basename(path), len(per))
     except Exception:
         return None, None
 
