@@ -110,11 +110,15 @@ def physical_gpu_index(local):
     return local
 
 
-def dist_setup(n_gpus):
+def dist_setup(n_gpus, need_cuda=True):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        if need_cuda:
+            raise RuntimeError("bench.py measures the CUDA path: no CUDA device is visible (there is no CPU implementation to fall back to)")
+        return rank, world, local     # --impl reference without a GPU: the scalar port on the host cores
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -465,7 +469,8 @@ def run_reference(args, rank, world, local):
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
             "config": {"workload": f"BASELINE configs[2]: {W}x{H} camera-pan sequence, temporal + variance + {args.levels} a-trous levels",
                        "width": W, "height": H, "atrous_levels": args.levels, "storage": "f16"}}
-    if not ref_available() or args.storage != "f16":
+    import torch as _torch
+    if not ref_available() or args.storage != "f16" or not _torch.cuda.is_available():
         cb = cpu_baseline(args)
         base.update({"value": cb["value"], "ms_per_step": cb["ms_per_frame_sample"], "dtype": "f32/f64 compute, fp16 storage",
                      "cpu_baseline": cb, "gpu_launches": 0,
@@ -572,7 +577,7 @@ def main():
     import __graft_entry__ as g
     if not (os.path.exists(os.path.join(ROOT, "svgf_b200", "libsvgf_b200.so")) and os.path.exists(os.path.join(ROOT, "oracle", "libsvgf_oracle.so"))):
         g.build()
-    rank, world, local = dist_setup(args.gpus)
+    rank, world, local = dist_setup(args.gpus, need_cuda=(args.impl != "reference"))
     if args.impl == "reference":
         line = run_reference(args, rank, world, local)
     elif args.mode == "bands":
@@ -585,8 +590,9 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":
