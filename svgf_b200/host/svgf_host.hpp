@@ -148,10 +148,14 @@ public:
         p.atrous_iterations = SpatialFilterSteps; p.depth_threshold = DepthThreshold; p.normal_threshold = NormalThreshold;
         p.history_cap = HistoryLength; p.phi_colour = PhiColour; p.phi_normal = PhiNormal;
         p.mesh_id_mode = MeshIdMode; p.flags = Flags;
+        p.reproj_mode = ReprojMode; p.variance_prefilter = VariancePrefilter;
         return p;
     }
     int MeshIdMode = SVGF_MESH_ID_INTENDED;
     uint32_t Flags = SVGF_FLAG_NONE;
+    // switches the reference has no counterpart for (include/svgf.h); the defaults are the reference's behaviour
+    int ReprojMode = SVGF_REPROJ_NEAREST_TRUNC;
+    int VariancePrefilter = SVGF_VARIANCE_PREFILTER_NONE;
 
 private:
     svgf_storage Storage;
