@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SVGF_ABI_VERSION 1
+#define SVGF_ABI_VERSION 2
 
 typedef struct svgf_ctx svgf_ctx;
 
@@ -90,6 +90,35 @@ typedef enum svgf_variance_prefilter { SVGF_VARIANCE_PREFILTER_NONE = 0, SVGF_VA
  * and for the parity tests that pin that identity). */
 #define SVGF_FLAG_NO_UNIFORM_TILES 8u
 
+/* svgf_frame / svgf_atrous: run every a-trous level from and to storage-format planes.  By default two or more consecutive
+ * levels run STAGED: the first level (packed kernel) writes its result as context-owned, pre-transformed "lattice planes"
+ * (fp32, clamped, pixel-pair interleaved, luminance attached - exactly what the next level's imageLoad would have produced,
+ * src/Filter.cuh:78-83), the following levels load their tiles from those with tensor-map TMA and only the last level
+ * writes the storage format again.  Results are within parity tolerance of the level-by-level path, not bit-identical
+ * (the uniform-normal shortcut folds the normal term into the exponent's constant there). */
+#define SVGF_FLAG_NO_STAGED_LEVELS 32u
+/* A/B variants of the a-trous level, both measured slower than the default: the persistent bulk-copy
+ * (cp.async.bulk) scalar kernel and the warp-specialised streaming kernel. */
+#define SVGF_FLAG_ATROUS_BULK 64u
+#define SVGF_FLAG_ATROUS_STREAM 128u
+/* Staged a-trous levels: launch every level as an ordinary stream-ordered kernel instead of with programmatic dependent
+ * launch (the default lets a level's prologue - barrier setup, tensor-map prefetch, uniform-tile test - overlap the
+ * previous level's tail). */
+#define SVGF_FLAG_NO_DEPENDENT_LAUNCH 256u
+
+/* Kernel family that ran an a-trous level (svgf_last_dispatch). */
+typedef enum svgf_dispatch_family {
+    SVGF_FAMILY_NONE = 0,
+    SVGF_FAMILY_BASIC = 1,          /* one thread per pixel: levels > 4, phi_normal < 32, phi_depth == 0, odd widths with the
+                                       prefilter, unaligned planes, SVGF_FLAG_BASIC_KERNELS - several times slower */
+    SVGF_FAMILY_PACKED = 2,         /* shared-memory tiles, packed FP32x2 arithmetic, storage format in and out */
+    SVGF_FAMILY_PACKED_STAGED = 3,  /* same, writing lattice planes for the level that follows */
+    SVGF_FAMILY_LATTICE = 4,        /* TMA-staged tiles from lattice planes */
+    SVGF_FAMILY_BULK = 5,           /* persistent cp.async.bulk kernel (odd widths; SVGF_FLAG_ATROUS_BULK) */
+    SVGF_FAMILY_STREAM = 6,         /* SVGF_FLAG_ATROUS_STREAM */
+    SVGF_FAMILY_FUSED01 = 7         /* SVGF_FLAG_FUSE_LEVELS_01 */
+} svgf_dispatch_family;
+
 /* Tunables.  Defaults (svgf_default_params) are the reference's members src/App.h:109-114, GUI ranges
  * src/GUI.cpp:988-993.  phi_depth / alpha_min / moments_alpha_min are additions whose defaults
  * reproduce the reference exactly. */
@@ -136,7 +165,8 @@ void svgf_default_params(svgf_params *p);
 
 /* Replaces application::ResizeRenderTextures()'s filter part (src/App.cu:742-778): the context owns only
  * scratch — the history shadow plane (race-free snapshot semantics for src/Filter.cuh:255 vs :400), two
- * compact guide planes and TMA descriptors.  `device` is a CUDA ordinal. */
+ * compact guide planes; the lattice planes and tensor maps of the staged a-trous levels are allocated on first use.
+ * `device` is a CUDA ordinal. */
 svgf_status svgf_create(svgf_ctx **out, int device, int width, int height, svgf_storage storage);
 void svgf_destroy(svgf_ctx *ctx);
 
@@ -177,8 +207,8 @@ svgf_status svgf_atrous(svgf_ctx *ctx, const svgf_params *params, const svgf_gbu
 svgf_status svgf_frame(svgf_ctx *ctx, const svgf_params *params, const svgf_gbuffer gbuf[2],
                        const svgf_frame_buffers *bufs, void *stream);
 
-/* The context caches a compact "guide" plane (depth, depth derivative, normal, mesh id: 16 B/px) per
- * G-buffer, keyed by the motion_depth pointer: svgf_temporal / svgf_frame build it for the current
+/* The context caches a compact "guide" plane (depth, depth derivative, normal, mesh id: 22 B/px) per
+ * G-buffer, keyed by the three plane pointers and pitches of the svgf_gbuffer: svgf_temporal / svgf_frame build it for the current
  * G-buffer, the following svgf_variance / svgf_atrous calls naming the same G-buffer reuse it, and the next
  * frame's temporal pass reads it as the previous-frame guide (the reference's two ping-ponged framebuffers,
  * src/App.cu:745-746, satisfy this by construction).  Call this after modifying a G-buffer in place outside
@@ -196,6 +226,11 @@ int svgf_last_cuda_error(const svgf_ctx *ctx);
 
 /* Number of kernel launches issued through this context so far (for bench accounting). */
 uint64_t svgf_launch_count(const svgf_ctx *ctx);
+
+/* Which kernel family (svgf_dispatch_family) ran each a-trous level of the most recent svgf_frame / svgf_atrous call:
+ * families[level] for level < min(return value, max_levels); returns the number of levels recorded.  Makes the slow
+ * per-pixel fallbacks (SVGF_FAMILY_BASIC) visible instead of silent. */
+int svgf_last_dispatch(const svgf_ctx *ctx, int32_t *families, int max_levels);
 
 /* Host-buffer path (what the end-to-end benchmark times, and what a caller without device memory of its own
  * uses): one frame's inputs host->device, svgf_frame, the result device->host.  `h_*` are pinned (or pageable)

@@ -13,7 +13,11 @@ SVGF_STORE_F16, SVGF_STORE_F32 = 0, 1
 SVGF_MESH_ID_INTENDED, SVGF_MESH_ID_REFERENCE_VACUOUS = 0, 1
 SVGF_FLAG_NO_GUIDE_CACHE, SVGF_FLAG_NO_LEVEL_FUSION, SVGF_FLAG_BASIC_KERNELS, SVGF_FLAG_NO_UNIFORM_TILES = 1, 2, 4, 8
 SVGF_FLAG_FUSE_LEVELS_01 = 16
-SVGF_ABI_VERSION = 1
+SVGF_FLAG_NO_STAGED_LEVELS, SVGF_FLAG_ATROUS_BULK, SVGF_FLAG_ATROUS_STREAM, SVGF_FLAG_NO_DEPENDENT_LAUNCH = 32, 64, 128, 256
+# svgf_dispatch_family (svgf_last_dispatch)
+SVGF_FAMILY_BASIC, SVGF_FAMILY_PACKED, SVGF_FAMILY_PACKED_STAGED, SVGF_FAMILY_LATTICE = 1, 2, 3, 4
+SVGF_FAMILY_BULK, SVGF_FAMILY_STREAM, SVGF_FAMILY_FUSED01 = 5, 6, 7
+SVGF_ABI_VERSION = 2
 
 
 class SvgfParams(C.Structure):
@@ -74,6 +78,7 @@ ABI = [
     ("svgf_profile_end", C.c_int, [C.c_void_p, C.POINTER(C.c_double * 3), C.POINTER(C.c_int)]),
     ("svgf_last_cuda_error", C.c_int, [C.c_void_p]),
     ("svgf_launch_count", C.c_uint64, [C.c_void_p]),
+    ("svgf_last_dispatch", C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int]),
     ("svgf_frame_host", C.c_int, [C.c_void_p, C.POINTER(SvgfParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 ]

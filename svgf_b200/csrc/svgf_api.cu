@@ -68,15 +68,17 @@ struct DeviceGuard {  // make the context's device current for the duration of a
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// Make sure a compact guide plane for `g` exists; returns its slot.
+// Make sure a compact guide plane for `g` exists; returns its slot.  A cached plane is reused only when all three plane
+// pointers and pitches match (svgf_ctx::GuideKey); contents changed in place under the same pointers need
+// svgf_invalidate_guide.
 svgf_status ensure_guide(svgf_ctx *c, const svgf_gbuffer *g, cudaStream_t s, int *slot) {
     for (int k = 0; k < 2; k++)
-        if (c->guide_key[k] == g->motion_depth) { *slot = k; return SVGF_OK; }
+        if (c->guide_key[k].matches(g)) { *slot = k; return SVGF_OK; }
     const int k = 1 - c->guide_cur;
     build_guide_kernel<<<grid_for(c), 256, 0, s>>>(view(c, g), c->guide[k], c->W, c->H);
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
-    c->guide_key[k] = g->motion_depth;
+    c->guide_key[k].set(g);
     c->guide_cur = k;
     *slot = k;
     return SVGF_OK;
@@ -91,9 +93,8 @@ svgf_status launch_temporal(svgf_ctx *c, const svgf_params *p, const svgf_gbuffe
     TemporalFused<F32> fused;
     fused.var_out = (CT *)fused_var_out;
     fused.worklist = c->worklist;
-    fused.counter = c->work_counter;
+    fused.counter = c->work_counter + c->work_parity;   // zeroed by the previous frame's sparse variance pass (or svgf_create / svgf_reset)
     fused.zero_normal_shortcut = p->phi_normal > 0.0f;
-    if (fused_var_out) SVGF_CUDA(c, cudaMemsetAsync(c->work_counter, 0, sizeof(unsigned int), s));
     TemporalArgs a;
     a.W = c->W; a.H = c->H;
     a.depth_threshold = p->depth_threshold; a.normal_threshold = p->normal_threshold;
@@ -104,12 +105,12 @@ svgf_status launch_temporal(svgf_ctx *c, const svgf_params *p, const svgf_gbuffe
     int prev_slot = -1;
     if (!(p->flags & SVGF_FLAG_NO_GUIDE_CACHE))
         for (int k = 0; k < 2; k++)
-            if (c->guide_key[k] == prev->motion_depth && c->guide_key[k] != nullptr) prev_slot = k;
+            if (c->guide_key[k].matches(prev)) prev_slot = k;
     // current-frame guide goes into the other slot
     int cur_slot = (prev_slot >= 0) ? 1 - prev_slot : 1 - c->guide_cur;
-    if (c->guide_key[cur_slot] == prev->motion_depth) c->guide_key[cur_slot] = nullptr;
+    c->guide_key[cur_slot].clear();
     const dim3 grid = grid_for(c);
-    const Guide pg = (prev_slot >= 0) ? c->guide[prev_slot] : Guide{nullptr, nullptr, nullptr};
+    const Guide pg = (prev_slot >= 0) ? c->guide[prev_slot] : Guide{nullptr, nullptr, nullptr, nullptr};
 #define SVGF_LAUNCH_TEMPORAL(PG, BL)                                                                                              \
     temporal_kernel<F32, PG, BL><<<grid, 256, 0, s>>>(a, view(c, cur), view(c, prev), pg, c->guide[cur_slot], (const CT *)prev_colour, \
                                                       (CT *)cur_colour, hist_prev, hist_out, (MT *)cur_mom, (const MT *)prev_mom, fused)
@@ -119,7 +120,7 @@ svgf_status launch_temporal(svgf_ctx *c, const svgf_params *p, const svgf_gbuffe
 #undef SVGF_LAUNCH_TEMPORAL
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
-    c->guide_key[cur_slot] = cur->motion_depth;
+    c->guide_key[cur_slot].set(cur);
     c->guide_cur = cur_slot;
     c->force_fail_next = false;
     return SVGF_OK;
@@ -152,21 +153,27 @@ svgf_status launch_variance(svgf_ctx *c, const svgf_params *p, int guide_slot, c
     return SVGF_OK;
 }
 
+// 7x7 estimate for the queued pixels; also publishes this frame's history lengths into the caller's plane and zeroes the
+// next frame's worklist counter (see the kernel).
 template <bool F32>
 svgf_status launch_variance_sparse(svgf_ctx *c, const svgf_params *p, int guide_slot, const void *in, const void *mom,
-                                   const uint8_t *hist, void *out, cudaStream_t s) {
+                                   const uint8_t *hist, uint8_t *hist_publish, void *out, cudaStream_t s) {
     using CT = typename ColourPlane<F32>::texel;
     using MT = typename MomentsPlane<F32>::texel;
     const SpatialArgs a = spatial_args(c, p, 0);
     const int grid = c->num_sms * 8;
+    const bool fold_publish = ((uintptr_t)hist_publish % 16) == 0;
+    unsigned int *cur = c->work_counter + c->work_parity, *next = c->work_counter + (c->work_parity ^ 1);
     if (a.nt.series)
         variance_sparse_kernel<F32, true><<<grid, 256, 0, s>>>(a, c->guide[guide_slot], (const CT *)in, (const MT *)mom, hist,
-                                                               c->worklist, c->work_counter, (CT *)out);
+                                                               c->worklist, cur, (CT *)out, fold_publish ? hist_publish : nullptr, next);
     else
         variance_sparse_kernel<F32, false><<<grid, 256, 0, s>>>(a, c->guide[guide_slot], (const CT *)in, (const MT *)mom, hist,
-                                                                c->worklist, c->work_counter, (CT *)out);
+                                                                c->worklist, cur, (CT *)out, fold_publish ? hist_publish : nullptr, next);
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
+    c->work_parity ^= 1;
+    if (!fold_publish) SVGF_CUDA(c, cudaMemcpyAsync(hist_publish, hist, (size_t)c->W * c->H, cudaMemcpyDeviceToDevice, s));
     return SVGF_OK;
 }
 
@@ -198,6 +205,42 @@ svgf_status launch_atrous_fused01(svgf_ctx *c, const svgf_params *p, int guide_s
     return atrous_fused01(c, F32, 5, t, guide_slot, in, out, hist_colour, s);
 }
 
+// AtrousTiledArgs of one level for the tiled kernel families (packed / lattice / bulk / stream); returns the series
+// terms the kernels are instantiated for: 3 = economised series (phi_normal >= 100, svgf_device.cuh economised_series3:
+// weight error <= 0.56 / (phiN log2e)^3 <= 1.9e-7 absolute), 5 = Taylor (32 <= phi_normal < 100).
+int tiled_args(const svgf_ctx *c, const svgf_params *p, int level, const float *var_blur, AtrousTiledArgs *t) {
+    const NormalTerm nt = make_normal_term(p->phi_normal);
+    t->W = c->W; t->H = c->H; t->level = level; t->tiles_x = t->tiles_y = 0;
+    t->uniform_tiles = (p->flags & SVGF_FLAG_NO_UNIFORM_TILES) ? 0 : 1;
+    t->var_blur = var_blur;
+    t->kL_scale = kLog2e / p->phi_colour;
+    t->kZ_scale = kLog2e / ((float)(1 << level) * p->phi_depth);
+    t->k1 = nt.k1; t->k2 = nt.k2; t->k3 = nt.k3; t->k4 = nt.k4; t->k5 = nt.k5;
+    if (p->phi_normal >= 100.0f) {
+        const NormalTerm e3 = economised_series3(p->phi_normal);
+        t->k1 = e3.k1; t->k2 = e3.k2; t->k3 = e3.k3;
+        return 3;
+    }
+    return 5;
+}
+
+// Preconditions of the tiled fast paths: levels 0..4, series-mode normal term (phi_normal >= 32), phi_depth > 0 (null
+// texels rely on |z - inf| * kZ = inf), 16-byte-aligned planes.  Everything else runs the per-pixel kernel - visibly:
+// svgf_last_dispatch reports the family chosen for every level.
+bool tiled_ok(const svgf_ctx *c, const svgf_params *p, int level) {
+    return level <= 4 && p->phi_normal >= 32.0f && p->phi_depth > 0.0f && !(p->flags & SVGF_FLAG_BASIC_KERNELS);
+}
+bool pair_ok(const svgf_ctx *c, const void *in, const void *out, const void *hist_colour) {
+    return c->W % 2 == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 16) == 0 && (!hist_colour || ((uintptr_t)hist_colour % 16) == 0);
+}
+
+void note_dispatch(svgf_ctx *c, int level, int family) {
+    if (level >= 0 && level < 16) {
+        c->dispatch[level] = family;
+        if (c->dispatch_n < level + 1) c->dispatch_n = level + 1;
+    }
+}
+
 template <bool F32>
 svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slot, const void *in, void *out,
                                 void *hist_colour, int level, cudaStream_t s) {
@@ -213,45 +256,36 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
         SVGF_CUDA(c, cudaGetLastError());
         a.var_blur = c->var_blur;
     }
-    // tiled fast path: levels 0..4, series-mode normal term (phi_normal >= 32), phi_depth > 0 (null texels rely on
-    // |z - inf| * kZ = inf); anything else runs the per-pixel kernel
-    // (the bulk copies need 16-byte-aligned row segments: even width for the 8-byte fp16 texels)
     // (with the variance prefilter only the packed three-term kernel has a fast path: phi_normal >= 100)
-    if (level <= 4 && a.nt.series && p->phi_depth > 0.0f && !(p->flags & SVGF_FLAG_BASIC_KERNELS) && (F32 || c->W % 2 == 0) &&
-        ((uintptr_t)in % 16) == 0 && !(prefilter && p->phi_normal < 100.0f)) {
+    if (tiled_ok(c, p, level) && (F32 || c->W % 2 == 0) && ((uintptr_t)in % 16) == 0 && !(prefilter && p->phi_normal < 100.0f)) {
         AtrousTiledArgs t;
-        t.W = c->W; t.H = c->H; t.level = level; t.tiles_x = t.tiles_y = 0;
-        t.uniform_tiles = (p->flags & SVGF_FLAG_NO_UNIFORM_TILES) ? 0 : 1;
-        t.var_blur = a.var_blur;
-        t.kL_scale = kLog2e / p->phi_colour;
-        t.kZ_scale = kLog2e / ((float)(1 << level) * p->phi_depth);
-        t.k1 = a.nt.k1; t.k2 = a.nt.k2; t.k3 = a.nt.k3; t.k4 = a.nt.k4; t.k5 = a.nt.k5;
-        // default: packed FP32x2 kernel (needs an even width and 16-byte-aligned planes for its pair loads/stores);
-        // SVGF_ATROUS_VARIANT=bulk selects the persistent bulk-copy (UBLKCP) scalar kernel for A/B measurements
-        static const char *variant = getenv("SVGF_ATROUS_VARIANT");
-        const bool want_bulk = variant && !strcmp(variant, "bulk") && !prefilter;      // the A/B variants have no prefilter path
-        const bool want_stream = variant && !strcmp(variant, "stream") && !prefilter;
-        const bool pair_ok = c->W % 2 == 0 && ((uintptr_t)out % 16) == 0 && (!hist_colour || ((uintptr_t)hist_colour % 16) == 0);
-        // default: packed FP32x2 tiled kernel.  SVGF_ATROUS_VARIANT=stream selects the warp-specialised streaming kernel
-        // (register sliding window; a third of the shared-memory traffic but two consumer warps per sub-partition —
-        // measured slower), =bulk the persistent bulk-copy scalar kernel
-        if (want_stream && pair_ok)
-            return atrous_stream(c, F32, p->phi_normal >= 100.0f ? 4 : 5, t, guide_slot, in, out, hist_colour, s);
-        if (!want_bulk && c->W % 2 == 0 && ((uintptr_t)out % 16) == 0 && (!hist_colour || ((uintptr_t)hist_colour % 16) == 0)) {
-            if (p->phi_normal >= 100.0f && (prefilter || !(variant && !strcmp(variant, "taylor4")))) {
-                // three-term economised series (svgf_device.cuh, economised_series3): one Horner step fewer per tap,
-                // weight error <= 0.56 / (phiN log2e)^3 <= 1.9e-7 absolute
-                const NormalTerm e3 = economised_series3(p->phi_normal);
-                t.k1 = e3.k1; t.k2 = e3.k2; t.k3 = e3.k3;
-                const int rows = 3;
-                return F32 ? atrous_packed_f32(c, 3, rows, t, guide_slot, in, out, hist_colour, s) : atrous_packed_f16(c, 3, rows, t, guide_slot, in, out, hist_colour, s);
-            }
-            const int terms = p->phi_normal >= 100.0f ? 4 : 5;
-            return F32 ? atrous_packed_f32(c, terms, 3, t, guide_slot, in, out, hist_colour, s) : atrous_packed_f16(c, terms, 3, t, guide_slot, in, out, hist_colour, s);
+        const int terms = tiled_args(c, p, level, a.var_blur, &t);
+        // A/B variants (measured slower): the warp-specialised streaming kernel and the persistent
+        // bulk-copy (UBLKCP) scalar kernel; both take the Taylor series only
+        const bool want_bulk = (p->flags & SVGF_FLAG_ATROUS_BULK) && !prefilter;
+        const bool want_stream = (p->flags & SVGF_FLAG_ATROUS_STREAM) && !prefilter;
+        if (want_bulk || want_stream) {
+            const NormalTerm nt = make_normal_term(p->phi_normal);
+            t.k1 = nt.k1; t.k2 = nt.k2; t.k3 = nt.k3; t.k4 = nt.k4; t.k5 = nt.k5;
         }
-        if (!prefilter) return atrous_tiled(c, F32, p->phi_normal >= 100.0f ? 4 : 5, t, guide_slot, in, out, hist_colour, s);
+        if (want_stream && pair_ok(c, in, out, hist_colour)) {
+            note_dispatch(c, level, kFamStream);
+            return atrous_stream(c, F32, p->phi_normal >= 100.0f ? 4 : 5, t, guide_slot, in, out, hist_colour, s);
+        }
+        if (!want_bulk && pair_ok(c, in, out, hist_colour)) {
+            note_dispatch(c, level, kFamPacked);
+            return F32 ? atrous_packed_f32(c, terms, 3, t, guide_slot, in, out, hist_colour, s)
+                       : atrous_packed_f16(c, terms, 3, t, guide_slot, in, out, hist_colour, s);
+        }
+        if (!prefilter) {
+            const NormalTerm nt = make_normal_term(p->phi_normal);
+            t.k1 = nt.k1; t.k2 = nt.k2; t.k3 = nt.k3; t.k4 = nt.k4; t.k5 = nt.k5;
+            note_dispatch(c, level, kFamBulk);
+            return atrous_tiled(c, F32, p->phi_normal >= 100.0f ? 4 : 5, t, guide_slot, in, out, hist_colour, s);
+        }
         // prefilter with planes the packed kernel cannot take: the per-pixel kernel below
     }
+    note_dispatch(c, level, kFamBasic);
     if (a.nt.series)
         atrous_kernel<F32, true><<<grid_for(c), 256, 0, s>>>(a, c->guide[guide_slot], (const CT *)in, (CT *)out, (CT *)hist_colour);
     else
@@ -261,9 +295,20 @@ svgf_status launch_atrous_level(svgf_ctx *c, const svgf_params *p, int guide_slo
     return SVGF_OK;
 }
 
+// Staged run (the default for two or more consecutive levels): the first level is the packed kernel writing its result
+// as lattice planes, every later level is the TMA-staged lattice kernel, and only the last one writes the storage
+// format again.  Needs what the packed kernel needs, plus levels <= 4 throughout and no variance prefilter (its blur
+// pass reads storage-format planes).
+bool staged_applicable(const svgf_ctx *c, const svgf_params *p, const void *a, const void *b, const void *hist_colour, int first, int n) {
+    if (n < 2 || first + n - 1 > 4 || !tiled_ok(c, p, first + n - 1)) return false;
+    if (p->flags & (SVGF_FLAG_NO_STAGED_LEVELS | SVGF_FLAG_FUSE_LEVELS_01 | SVGF_FLAG_ATROUS_BULK | SVGF_FLAG_ATROUS_STREAM)) return false;
+    if (p->variance_prefilter != SVGF_VARIANCE_PREFILTER_NONE) return false;
+    return pair_ok(c, a, b, hist_colour) && !c->lat.failed;
+}
+
 // Number of buffer swaps run_atrous makes for levels first..first+n-1: one per launch (n, or n - 1 when levels 0 and 1
 // go out as one fused launch).  svgf_frame needs it up front to aim the variance output so that the result lands in
-// filter[0].
+// filter[0].  A staged run reports n: its result is written where n ping-pong hops would have left it.
 int atrous_hops(const svgf_ctx *c, const svgf_params *p, const void *a, const void *b, const void *hist_colour, int first, int n) {
     const bool fuse = first == 0 && n >= 2 &&
                       (c->storage == SVGF_STORE_F32 ? fused01_applicable<true>(c, p, a, b, hist_colour)
@@ -271,12 +316,44 @@ int atrous_hops(const svgf_ctx *c, const svgf_params *p, const void *a, const vo
     return fuse ? n - 1 : n;
 }
 
+svgf_status run_atrous_staged(svgf_ctx *c, const svgf_params *p, int guide_slot, void *a, void *b, void *hist_colour, int first,
+                              int n, void **result, cudaStream_t s) {
+    const bool f32 = c->storage == SVGF_STORE_F32;
+    void *final_dst = (n & 1) ? b : a;
+    AtrousTiledArgs t;
+    int terms = tiled_args(c, p, first, nullptr, &t);
+    note_dispatch(c, first, kFamPackedStaged);
+    svgf_status st = f32 ? atrous_packed_staged_f32(c, terms, t, guide_slot, a, 0, first == 0 ? hist_colour : nullptr, s)
+                         : atrous_packed_staged_f16(c, terms, t, guide_slot, a, 0, first == 0 ? hist_colour : nullptr, s);
+    if (st) return st;
+    const bool pdl = !(p->flags & SVGF_FLAG_NO_DEPENDENT_LAUNCH);
+    int src = 0;
+    for (int l = first + 1; l < first + n; l++) {
+        terms = tiled_args(c, p, l, nullptr, &t);
+        void *out = (l == first + n - 1) ? final_dst : nullptr;
+        note_dispatch(c, l, kFamLattice);
+        st = f32 ? atrous_lattice_f32(c, terms, t, guide_slot, src, out, pdl, s) : atrous_lattice_f16(c, terms, t, guide_slot, src, out, pdl, s);
+        if (st) return st;
+        src = 1 - src;
+    }
+    if (result) *result = final_dst;
+    return SVGF_OK;
+}
+
 // Levels first..first+n-1, ping-ponging a -> b -> a ...; *result = last output (or `a` when n == 0).
 svgf_status run_atrous(svgf_ctx *c, const svgf_params *p, int guide_slot, void *a, void *b, void *hist_colour, int first,
                        int n, void **result, cudaStream_t s) {
     void *in = a, *out = b;
     const bool f32 = c->storage == SVGF_STORE_F32;
+    c->dispatch_n = 0;
+    if (staged_applicable(c, p, a, b, hist_colour, first, n)) {
+        const svgf_status st = lattice_prepare(c, s);
+        if (st == SVGF_OK) return run_atrous_staged(c, p, guide_slot, a, b, hist_colour, first, n, result, s);
+        if (st != SVGF_UNSUPPORTED) return st;      // no tensor maps available: level by level below
+    }
     if (first == 0 && n >= 2 && atrous_hops(c, p, a, b, hist_colour, first, n) == n - 1) {
+        note_dispatch(c, 0, kFamFused01);
+        note_dispatch(c, 1, kFamFused01);
         svgf_status st = f32 ? launch_atrous_fused01<true>(c, p, guide_slot, in, out, hist_colour, s)
                              : launch_atrous_fused01<false>(c, p, guide_slot, in, out, hist_colour, s);
         if (st) return st;
@@ -351,10 +428,12 @@ svgf_status svgf_create(svgf_ctx **out, int device, int width, int height, svgf_
         e = cudaMalloc(&c->guide[k].n, n * sizeof(float4));
         if (e == cudaSuccess) e = cudaMalloc(&c->guide[k].dz, n * sizeof(float));
         if (e == cudaSuccess) e = cudaMalloc(&c->guide[k].mid, n * sizeof(unsigned short));
+        if (e == cudaSuccess) e = cudaMalloc(&c->guide[k].seg, (size_t)((width + 31) / 32) * height * sizeof(float4));
     }
     c->num_sms = prop.multiProcessorCount;
     if (e == cudaSuccess) e = cudaMalloc(&c->worklist, n * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMalloc(&c->work_counter, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->work_counter, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(c->work_counter, 0, 2 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(c->hist_shadow, 0, n);
     if (e != cudaSuccess) { svgf_destroy(c); return SVGF_CUDA_ERROR; }
     *out = c;
@@ -368,7 +447,8 @@ void svgf_destroy(svgf_ctx *c) {
     cudaFree(c->worklist);
     cudaFree(c->work_counter);
     cudaFree(c->var_blur);
-    for (int k = 0; k < 2; k++) { cudaFree(c->guide[k].n); cudaFree(c->guide[k].dz); cudaFree(c->guide[k].mid); }
+    for (int k = 0; k < 2; k++) { cudaFree(c->guide[k].n); cudaFree(c->guide[k].dz); cudaFree(c->guide[k].mid); cudaFree(c->guide[k].seg); }
+    lattice_destroy(c);
     if (c->prof_ev) {
         for (int i = 0; i < svgf_ctx::kMaxProf * 4; i++) cudaEventDestroy(c->prof_ev[i]);
         delete[] c->prof_ev;
@@ -381,7 +461,7 @@ void svgf_destroy(svgf_ctx *c) {
         if (c->hp.ev_done[k]) cudaEventDestroy(c->hp.ev_done[k]);
     }
     if (c->hp.ev_out) cudaEventDestroy(c->hp.ev_out);
-    for (int k = 0; k < 2; k++) { cudaFree(c->hp.render[k]); cudaFree(c->hp.moments[k]); cudaFree(c->hp.filter[k]); }
+    for (int k = 0; k < 2; k++) { cudaFree(c->hp.moments[k]); cudaFree(c->hp.filter[k]); }
     cudaFree(c->hp.history);
     delete c;
 }
@@ -391,7 +471,15 @@ uint64_t svgf_launch_count(const svgf_ctx *c) { return c ? c->launches : 0; }
 
 void svgf_invalidate_guide(svgf_ctx *c) {
     if (!c) return;
-    c->guide_key[0] = c->guide_key[1] = nullptr;
+    c->guide_key[0].clear();
+    c->guide_key[1].clear();
+}
+
+int svgf_last_dispatch(const svgf_ctx *c, int32_t *families, int max_levels) {
+    if (!c) return 0;
+    for (int i = 0; i < c->dispatch_n && i < max_levels; i++)
+        if (families) families[i] = c->dispatch[i];
+    return c->dispatch_n;
 }
 
 svgf_status svgf_reset(svgf_ctx *c, const svgf_frame_buffers *b, void *stream) {
@@ -407,6 +495,7 @@ svgf_status svgf_reset(svgf_ctx *c, const svgf_frame_buffers *b, void *stream) {
         if (b->history) SVGF_CUDA(c, cudaMemsetAsync(b->history, 0, (size_t)c->W * c->H, s));
     }
     SVGF_CUDA(c, cudaMemsetAsync(c->hist_shadow, 0, (size_t)c->W * c->H, s));
+    SVGF_CUDA(c, cudaMemsetAsync(c->work_counter, 0, 2 * sizeof(unsigned int), s));
     svgf_invalidate_guide(c);
     c->force_fail_next = true;
     return SVGF_OK;
@@ -506,10 +595,9 @@ svgf_status svgf_frame(svgf_ctx *c, const svgf_params *p, const svgf_gbuffer gbu
         if (st) return st;
     } else {
         // 7x7 estimate for the queued pixels only, then publish this frame's history lengths
-        st = f32 ? launch_variance_sparse<true>(c, p, slot, b->render[P], b->moments[P], c->hist_shadow, v_out, s)
-                 : launch_variance_sparse<false>(c, p, slot, b->render[P], b->moments[P], c->hist_shadow, v_out, s);
+        st = f32 ? launch_variance_sparse<true>(c, p, slot, b->render[P], b->moments[P], c->hist_shadow, b->history, v_out, s)
+                 : launch_variance_sparse<false>(c, p, slot, b->render[P], b->moments[P], c->hist_shadow, b->history, v_out, s);
         if (st) return st;
-        SVGF_CUDA(c, cudaMemcpyAsync(b->history, c->hist_shadow, (size_t)c->W * c->H, cudaMemcpyDeviceToDevice, s));
     }
     prof_mark(c, 2, s);
     void *result = nullptr;
@@ -574,32 +662,44 @@ svgf_status svgf_frame_host(svgf_ctx *c, const svgf_params *p, const void *h_nor
     svgf_ctx::HostPath &hp = c->hp;
     constexpr int R = svgf_ctx::HostPath::kRing;
     if (!hp.ready) {
+        // a retry after a failed allocation keeps what is already there (every pointer / handle starts out null)
+        auto dmalloc = [&](void **p, size_t bytes) { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
+        auto mkevent = [&](cudaEvent_t *e) { return *e ? cudaSuccess : cudaEventCreateWithFlags(e, cudaEventDisableTiming); };
         for (int k = 0; k < R; k++) {
-            SVGF_CUDA(c, cudaMalloc(&hp.normal[k], n * 8));
-            SVGF_CUDA(c, cudaMalloc(&hp.uv[k], n * 8));
-            SVGF_CUDA(c, cudaMalloc(&hp.motion[k], n * 16));
-            SVGF_CUDA(c, cudaMalloc(&hp.noisy[k], colour_bytes(c)));
-            SVGF_CUDA(c, cudaEventCreateWithFlags(&hp.ev_in[k], cudaEventDisableTiming));
-            SVGF_CUDA(c, cudaEventCreateWithFlags(&hp.ev_done[k], cudaEventDisableTiming));
+            SVGF_CUDA(c, dmalloc(&hp.normal[k], n * 8));
+            SVGF_CUDA(c, dmalloc(&hp.uv[k], n * 8));
+            SVGF_CUDA(c, dmalloc(&hp.motion[k], n * 16));
+            SVGF_CUDA(c, dmalloc(&hp.noisy[k], colour_bytes(c)));
+            SVGF_CUDA(c, mkevent(&hp.ev_in[k]));
+            SVGF_CUDA(c, mkevent(&hp.ev_done[k]));
         }
         for (int k = 0; k < 2; k++) {
-            SVGF_CUDA(c, cudaMalloc(&hp.render[k], colour_bytes(c)));
-            SVGF_CUDA(c, cudaMalloc(&hp.moments[k], moments_bytes(c)));
-            SVGF_CUDA(c, cudaMalloc(&hp.filter[k], colour_bytes(c)));
+            SVGF_CUDA(c, dmalloc(&hp.moments[k], moments_bytes(c)));
+            SVGF_CUDA(c, dmalloc(&hp.filter[k], colour_bytes(c)));
         }
-        SVGF_CUDA(c, cudaMalloc(&hp.history, n));
-        SVGF_CUDA(c, cudaEventCreateWithFlags(&hp.ev_out, cudaEventDisableTiming));
-        SVGF_CUDA(c, cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
-        SVGF_CUDA(c, cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+        SVGF_CUDA(c, dmalloc((void **)&hp.history, n));
+        SVGF_CUDA(c, mkevent(&hp.ev_out));
+        if (!hp.s_in) SVGF_CUDA(c, cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+        if (!hp.s_out) SVGF_CUDA(c, cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
         hp.frame = 0;
         hp.ready = true;
         reset = 1;
     }
     svgf_frame_buffers b;
-    for (int k = 0; k < 2; k++) { b.render[k] = hp.render[k]; b.moments[k] = hp.moments[k]; b.filter[k] = hp.filter[k]; }
+    // RenderBuffer[P] IS the ring slot the noisy radiance was uploaded into (the temporal pass works in place and level 0
+    // leaves the next frame's colour history there); RenderBuffer[1 - P] is the previous frame's slot.  No device copy.
+    for (int k = 0; k < 2; k++) { b.moments[k] = hp.moments[k]; b.filter[k] = hp.filter[k]; }
     b.history = hp.history;
     if (reset) {
+        if (hp.frame) {   // a sequence is in flight: drain it before its ring slots are reused from frame 0
+            SVGF_CUDA(c, cudaStreamSynchronize(hp.s_in));
+            SVGF_CUDA(c, cudaStreamSynchronize(s));
+            SVGF_CUDA(c, cudaStreamSynchronize(hp.s_out));
+        }
+        hp.frame = 0;
         hp.ping_pong = 0;
+        b.render[0] = nullptr;            // about to be overwritten by the upload
+        b.render[1] = hp.noisy[R - 1];    // "previous colour" of the first frame (slot of frame -1)
         if ((st = svgf_reset(c, &b, s))) return st;
     }
     const uint64_t t = hp.frame;
@@ -617,7 +717,8 @@ svgf_status svgf_frame_host(svgf_ctx *c, const svgf_params *p, const void *h_nor
 
     // kernels, on the caller's stream
     SVGF_CUDA(c, cudaStreamWaitEvent(s, hp.ev_in[k], 0));
-    SVGF_CUDA(c, cudaMemcpyAsync(hp.render[P], hp.noisy[k], colour_bytes(c), cudaMemcpyDeviceToDevice, s));
+    b.render[P] = hp.noisy[k];
+    b.render[1 - P] = hp.noisy[kprev];
     svgf_gbuffer g[2];
     const int slot_of[2] = {P == 0 ? k : kprev, P == 0 ? kprev : k};   // g[P] = this frame's slot, g[1-P] = last frame's
     for (int q = 0; q < 2; q++) {
@@ -628,7 +729,7 @@ svgf_status svgf_frame_host(svgf_ctx *c, const svgf_params *p, const void *h_nor
     }
     // the contents of ring slot k have just changed under the same pointer
     for (int q = 0; q < 2; q++)
-        if (c->guide_key[q] == hp.motion[k]) c->guide_key[q] = nullptr;
+        if (c->guide_key[q].motion == hp.motion[k]) c->guide_key[q].clear();
     if ((st = svgf_frame(c, p, g, &b, s))) return st;
     SVGF_CUDA(c, cudaEventRecord(hp.ev_done[k], s));
 

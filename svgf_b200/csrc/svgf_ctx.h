@@ -2,8 +2,10 @@
 // Every family is compiled in its own translation unit (svgf_tu_*.cu) so that the library builds in parallel; the
 // entry points are plain functions selected at run time by svgf_api.cu.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only: the driver entry point is fetched at run time, no libcuda link)
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 
 #include "../../include/svgf.h"
@@ -14,16 +16,44 @@ struct svgf_ctx {
     int device = 0, W = 0, H = 0;
     svgf_storage storage = SVGF_STORE_F16;
     uint8_t *hist_shadow = nullptr;       // this frame's history lengths until published (D3)
-    svgf::Guide guide[2] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // compact guide planes, ping-pong
+    svgf::Guide guide[2] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};  // compact guide planes, ping-pong
     int num_sms = 148;
     unsigned int *worklist = nullptr;     // indices of short-history pixels queued by the fused temporal pass
-    unsigned int *work_counter = nullptr;
+    unsigned int *work_counter = nullptr; // two counters used alternately: the sparse variance pass of frame t zeroes frame t+1's
+    int work_parity = 0;
     float *var_blur = nullptr;            // 3x3-blurred variance of the current a-trous input (GAUSS3 prefilter), allocated on first use
-    const void *guide_key[2] = {nullptr, nullptr};  // motion_depth pointer of the G-buffer each plane was built from
+    // identity of the G-buffer each guide plane was built from: the three plane pointers, their pitches and the caller's
+    // generation counter (svgf_gbuffer has none, so svgf_invalidate_guide / a changed pointer or pitch are the signals)
+    struct GuideKey {
+        const void *motion = nullptr, *normal = nullptr, *uv = nullptr;
+        size_t motion_pitch = 0, normal_pitch = 0, uv_pitch = 0;
+        bool matches(const svgf_gbuffer *g) const {
+            return motion && g->motion_depth == motion && g->normal_mat == normal && g->uv_inst == uv && g->motion_pitch == motion_pitch &&
+                   g->normal_pitch == normal_pitch && g->uv_pitch == uv_pitch;
+        }
+        void set(const svgf_gbuffer *g) {
+            motion = g->motion_depth; normal = g->normal_mat; uv = g->uv_inst;
+            motion_pitch = g->motion_pitch; normal_pitch = g->normal_pitch; uv_pitch = g->uv_pitch;
+        }
+        void clear() { motion = nullptr; }
+    } guide_key[2];
     int guide_cur = 0;                    // slot of the most recently built guide
     bool force_fail_next = false;         // set by svgf_reset
     int last_err = 0;
     uint64_t launches = 0;
+    // lattice planes of the TMA-staged a-trous levels (svgf_kernels_lattice.cuh), allocated on first use
+    struct Lattice {
+        bool ready = false, failed = false;
+        int pitch_pairs = 0, rows = 0;
+        size_t npairs = 0;
+        svgf::LatticeColour sc[2] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+        svgf::LatticeNormals sn = {nullptr, nullptr};
+        // tensor maps per level 1..4 (index 0 unused) and plane: sc[0].c0 c1 lz, sc[1].c0 c1 lz, sn.n0, sn.n1
+        CUtensorMap map[5][8];
+    } lat;
+    // which kernel family ran each a-trous level of the last svgf_frame / svgf_atrous call (svgf_last_dispatch)
+    int dispatch[16] = {};
+    int dispatch_n = 0;
     // stage profiling (svgf_profile_*): events around temporal / variance / a-trous inside svgf_frame
     bool profiling = false;
     static constexpr int kMaxProf = 4096;
@@ -57,6 +87,31 @@ inline svgf_status svgf_cuda_fail(svgf_ctx *c, cudaError_t e) {
     } while (0)
 
 namespace svgf {
+// Raises a kernel's dynamic shared-memory limit once per device.  `done` is a per-instantiation bit set indexed by device
+// ordinal (ordinals >= 64 simply repeat the call, which is harmless); concurrent contexts may race to set the same bit
+// with the same value.
+template <typename K> inline cudaError_t configure_smem_once(std::atomic<unsigned long long> &done, int device, K kern, size_t bytes) {
+    const unsigned long long bit = device < 64 ? (1ull << device) : 0ull;
+    if (bit && (done.load(std::memory_order_acquire) & bit)) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess && bit) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
+// svgf_dispatch_family values (include/svgf.h)
+enum { kFamBasic = 1, kFamPacked = 2, kFamPackedStaged = 3, kFamLattice = 4, kFamBulk = 5, kFamStream = 6, kFamFused01 = 7 };
+
+// svgf_tma.cu: allocate the lattice planes and encode their tensor maps (idempotent)
+svgf_status lattice_prepare(svgf_ctx *c, cudaStream_t s);
+void lattice_destroy(svgf_ctx *c);
+// first level of a staged run: the packed kernel writing lattice planes (set `dst`) instead of `out`
+svgf_status atrous_packed_staged_f16(svgf_ctx *c, int terms, const AtrousTiledArgs &a, int guide_slot, const void *in, int dst, void *hist_colour, cudaStream_t s);
+svgf_status atrous_packed_staged_f32(svgf_ctx *c, int terms, const AtrousTiledArgs &a, int guide_slot, const void *in, int dst, void *hist_colour, cudaStream_t s);
+// lattice level a.level (1..4): planes sc[src] -> sc[1 - src], or -> `out` in the storage format when out != nullptr;
+// pdl: launch with programmatic stream serialisation (the kernel's prologue overlaps the previous level's tail)
+svgf_status atrous_lattice_f16(svgf_ctx *c, int terms, const AtrousTiledArgs &a, int guide_slot, int src, void *out, bool pdl, cudaStream_t s);
+svgf_status atrous_lattice_f32(svgf_ctx *c, int terms, const AtrousTiledArgs &a, int guide_slot, int src, void *out, bool pdl, cudaStream_t s);
+
 // one a-trous level (a.level = 0..4) / levels 0+1 fused; terms = series terms of the normal weight (3, 4 or 5);
 // rows = outputs per thread and column of the packed kernel (3, or 4 with terms == 3)
 svgf_status atrous_packed_f16(svgf_ctx *c, int terms, int rows, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out, void *hist_colour, cudaStream_t s);

@@ -73,11 +73,31 @@ __device__ __forceinline__ float mix_rn(float x, float y, float a) {
 //   n   : float4 (z', nx, ny, nz)   z' = GetDepth: 0 -> 1e30 (src/Filter.cuh:199-207)      16 B/px
 //   dz  : float  depth derivative (0 for background)                                         4 B/px
 //   mid : fp16 bits of uv.w, the instance index (GBuffer.frag:77)                            2 B/px
+//   seg : float4 per 32-pixel ROW SEGMENT (x / 32, y): (nx, ny, nz, state) - state 0: the segment holds only background
+//         texels (z' = 1e30) or lies outside the image, 1: all its non-background texels carry the normal xyz, 2: mixed.
+//         Lets an a-trous tile decide "one normal everywhere" from 96 entries instead of 1000+ texels
+//         (svgf_kernels_lattice.cuh); background texels are wildcards because their weight is 0 through z'.
 struct Guide {
     float4 *n;
     float *dz;
     unsigned short *mid;
+    float4 *seg;
 };
+// Padding (pixels / rows) around the context-owned lattice planes of svgf_kernels_lattice.cuh: the widest halo, 2 * 2^4.
+constexpr int kLatPadX = 32, kLatPadY = 32;
+
+// One warp = one 32-pixel row segment (lane = pixel).  `gn` is the lane's guide texel (z', nx, ny, nz); lanes outside the
+// image pass valid = false.  Returns the segment's map entry (identical in every lane).
+__device__ __forceinline__ float4 segment_state(float4 gn, bool valid) {
+    const bool solid = valid && gn.x != 1e30f;
+    const unsigned m = __ballot_sync(0xffffffffu, solid);
+    if (m == 0) return make_float4(0.f, 0.f, 0.f, 0.0f);
+    const int leader = __ffs(m) - 1;
+    const float rx = __shfl_sync(0xffffffffu, gn.y, leader), ry = __shfl_sync(0xffffffffu, gn.z, leader),
+                rz = __shfl_sync(0xffffffffu, gn.w, leader);
+    const bool same = !solid || (gn.y == rx && gn.z == ry && gn.w == rz);   // compared as floats: +0 == -0, NaN never matches
+    return make_float4(rx, ry, rz, __all_sync(0xffffffffu, same) ? 1.0f : 2.0f);
+}
 struct GuideTexel {
     float4 n;
     float dz;
@@ -168,5 +188,30 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 // read-only, L1-allocating vector loads
 template <typename T> __device__ __forceinline__ T ldg(const T *p) { return __ldg(p); }
+
+// ---- lattice planes (svgf_kernels_lattice.cuh): a level's input pre-transformed by its producer ---------------------
+// destination planes of a level whose successor is a lattice level (origin of the PADDED allocation)
+struct LatticeColour { float4 *c0, *c1, *lz; };
+struct LatticeNormals { float4 *n0; float2 *n1; };
+
+__device__ __forceinline__ size_t lattice_index(int gx, int gy, int pitch_pairs) {
+    return (size_t)(gy + kLatPadY) * pitch_pairs + ((gx + kLatPadX) >> 1);
+}
+
+// What the next level's imageLoad would see of a stored result (src/Filter.cuh:78-83 after :618): round through the
+// storage format, clamp, luminance.
+template <bool F32>
+__device__ __forceinline__ void lattice_requantise(float4 &o) {
+    if (!F32) o = ColourPlane<false>::decode(ColourPlane<false>::encode(o));
+    o = make_float4(__saturatef(o.x), __saturatef(o.y), __saturatef(o.z), __saturatef(o.w));
+}
+template <bool F32>
+__device__ __forceinline__ void lattice_store_pair(const LatticeColour &dst, size_t li, float4 o0, float4 o1, float2 z) {
+    lattice_requantise<F32>(o0);
+    lattice_requantise<F32>(o1);
+    dst.c0[li] = make_float4(o0.x, o1.x, o0.y, o1.y);
+    dst.c1[li] = make_float4(o0.z, o1.z, o0.w, o1.w);
+    dst.lz[li] = make_float4(luminance(o0.x, o0.y, o0.z), luminance(o1.x, o1.y, o1.z), z.x, z.y);
+}
 
 }  // namespace svgf

@@ -44,10 +44,17 @@ struct TemporalArgs {
 // pass has not seen) ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) build_guide_kernel(GBufView g, Guide guide, int W, int H) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= W || y >= H) return;
-    const GuideTexel t = make_guide(g.mot(x, y), g.nrm(x, y), g.uvw(x, y));
-    const size_t i = (size_t)y * W + x;
-    guide.n[i] = t.n; guide.dz[i] = t.dz; guide.mid[i] = t.mid;
+    if (y >= H) return;                                   // uniform per warp
+    const bool inb = x < W;
+    float4 gn = make_float4(kBackgroundZ, 0.f, 0.f, 0.f);
+    if (inb) {
+        const GuideTexel t = make_guide(g.mot(x, y), g.nrm(x, y), g.uvw(x, y));
+        const size_t i = (size_t)y * W + x;
+        guide.n[i] = t.n; guide.dz[i] = t.dz; guide.mid[i] = t.mid;
+        gn = t.n;
+    }
+    const float4 sg = segment_state(gn, inb);
+    if ((threadIdx.x & 31) == 0) guide.seg[(size_t)y * gridDim.x + blockIdx.x] = sg;
 }
 
 // ---- temporal reprojection + accumulation: reference filter::TemporalFilter (src/Filter.cuh:359-404) with
@@ -66,11 +73,13 @@ temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, Guide prev_guide, G
     const bool inb = (x < a.W && y < a.H);
     bool queue = false;
     const size_t i = (size_t)y * a.W + x;
+    float4 seg_n = make_float4(kBackgroundZ, 0.f, 0.f, 0.f);
     if (inb) {
 
     const float4 mv = cur.mot(x, y);
     const GuideTexel g = make_guide(mv, cur.nrm(x, y), cur.uvw(x, y));
     cur_guide.n[i] = g.n; cur_guide.dz[i] = g.dz; cur_guide.mid[i] = g.mid;
+    seg_n = g.n;
     const float4 c = clamp01(ColourPlane<F32>::decode(colour[i]));            // :370
 
     float3 pc = make_float3(0.f, 0.f, 0.f);
@@ -166,6 +175,10 @@ temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, Guide prev_guide, G
         queue = (h < 4) && !zero_n;
         fused.var_out[i] = (h < 4 && zero_n) ? ColourPlane<F32>::encode(make_float4(0.f, 0.f, 0.f, 0.f)) : enc;
     }
+    }
+    if (y < a.H) {         // this warp's 32-pixel row segment of the guide's segment map (uniform per warp)
+        const float4 sg = segment_state(seg_n, inb);
+        if ((threadIdx.x & 31) == 0) cur_guide.seg[(size_t)y * gridDim.x + blockIdx.x] = sg;
     }
     if (fused.var_out) {   // warp-aggregated append of the short-history pixels
         const unsigned int m = __ballot_sync(0xffffffffu, queue);
@@ -300,13 +313,27 @@ variance_kernel(SpatialArgs a, Guide guide, const typename ColourPlane<F32>::tex
 
 // Sparse form (svgf_frame): only the pixels the temporal pass queued (history < 4, non-zero normal); every other
 // pixel of `out` was already written by the temporal pass.  Grid-stride over the worklist.
+// Two chores ride along so that a frame needs no memset and no copy node between its kernels: the grid publishes this
+// frame's history lengths (hist -> hist_publish, 16 bytes per thread and iteration; the caller's plane was last read by
+// the temporal pass that precedes this launch in the stream) and zeroes the OTHER worklist counter, the one the next
+// frame's temporal pass will append to.
 template <bool F32, bool SERIES>
 __global__ void __launch_bounds__(256)
 variance_sparse_kernel(SpatialArgs a, Guide guide, const typename ColourPlane<F32>::texel *__restrict__ in,
                        const typename MomentsPlane<F32>::texel *__restrict__ mom, const uint8_t *__restrict__ hist,
                        const unsigned int *__restrict__ worklist, const unsigned int *__restrict__ counter,
-                       typename ColourPlane<F32>::texel *__restrict__ out) {
+                       typename ColourPlane<F32>::texel *__restrict__ out, uint8_t *__restrict__ hist_publish,
+                       unsigned int *__restrict__ next_counter) {
     const unsigned int n = *counter;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsize = (size_t)gridDim.x * blockDim.x;
+    if (gtid == 0 && next_counter) *next_counter = 0;
+    if (hist_publish) {    // both planes 16-byte aligned (checked by the host)
+        const size_t bytes = (size_t)a.W * a.H, nv = bytes >> 4;
+        const uint4 *src = reinterpret_cast<const uint4 *>(hist);
+        uint4 *dst = reinterpret_cast<uint4 *>(hist_publish);
+        for (size_t k = gtid; k < nv; k += gsize) dst[k] = src[k];
+        if (gtid < (bytes & 15)) hist_publish[(nv << 4) + gtid] = hist[(nv << 4) + gtid];
+    }
     for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const unsigned int i = worklist[k];
         const int y = (int)(i / (unsigned int)a.W), x = (int)(i - (unsigned int)y * (unsigned int)a.W);

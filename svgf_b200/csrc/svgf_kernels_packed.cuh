@@ -234,11 +234,14 @@ __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[R], const PkCentre (&C)[R
 
 // PREF: the centre variance comes from the pre-blurred plane a.var_blur (SVGF_VARIANCE_PREFILTER_GAUSS3); a template
 // parameter because even a never-taken branch here costs the register-capped default kernel 4 %
-template <bool F32, int STEP, int TERMS, int R = kPkRows, bool PREF = false, bool HC = false>
+// STAGED: this level feeds a lattice level (svgf_kernels_lattice.cuh): instead of `out` in the storage format it writes
+// the successor's pre-transformed input planes `lc` (result rounded through the storage format, clamped, luminance, depth)
+// and, once per frame, the pair-interleaved normal planes `ln` - all from values the thread already holds.
+template <bool F32, int STEP, int TERMS, int R = kPkRows, bool PREF = false, bool HC = false, bool STAGED = false>
 __global__ void __launch_bounds__(kPkPairs * (PackedGeom<STEP>::tile_rows / R), 2)
 atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, const float *__restrict__ guide_dz,
                      const typename ColourPlane<F32>::texel *__restrict__ in, typename ColourPlane<F32>::texel *__restrict__ out,
-                     typename ColourPlane<F32>::texel *__restrict__ hist_colour) {
+                     typename ColourPlane<F32>::texel *__restrict__ hist_colour, LatticeColour lc, LatticeNormals ln, int lat_pitch_pairs) {
     using G = PackedGeom<STEP>;
     constexpr int kThreads = kPkPairs * (G::tile_rows / R);   // R = 3: 256 threads, R = 4: 192
     static_assert(G::tile_rows % R == 0, "row groups must tile the 12 rows");
@@ -366,13 +369,19 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
         if (!live1[j]) o1 = make_float4(cr.y, cg.y, cb.y, cv.y);
         const CT e0 = ColourPlane<F32>::encode(o0), e1 = ColourPlane<F32>::encode(o1);
         const bool h0 = (a.level == 0) && hist_colour && live0[j], h1 = (a.level == 0) && hist_colour && live1[j];
+        if (STAGED) {
+            const size_t li = lattice_index(gx, gy, lat_pitch_pairs);
+            lattice_store_pair<F32>(lc, li, o0, o1, C[j].zc);
+            ln.n0[li] = make_float4(C[j].nx.x, C[j].nx.y, C[j].ny.x, C[j].ny.y);
+            ln.n1[li] = C[j].nz;
+        }
         if (F32) {
-            out[gi] = e0; out[gi + 1] = e1;
+            if (!STAGED) { out[gi] = e0; out[gi + 1] = e1; }
             if (h0) hist_colour[gi] = e0;
             if (h1) hist_colour[gi + 1] = e1;
         } else {
             const uint2 u0 = *reinterpret_cast<const uint2 *>(&e0), u1 = *reinterpret_cast<const uint2 *>(&e1);
-            *reinterpret_cast<uint4 *>(out + gi) = make_uint4(u0.x, u0.y, u1.x, u1.y);
+            if (!STAGED) *reinterpret_cast<uint4 *>(out + gi) = make_uint4(u0.x, u0.y, u1.x, u1.y);
             if (h0 && h1) *reinterpret_cast<uint4 *>(hist_colour + gi) = make_uint4(u0.x, u0.y, u1.x, u1.y);
             else {
                 if (h0) hist_colour[gi] = e0;

@@ -9,11 +9,8 @@ svgf_status launch_atrous_fused01_t(svgf_ctx *c, const AtrousTiledArgs &t, int g
                                     cudaStream_t s) {
     using CT = typename ColourPlane<F32>::texel;
     auto kern = atrous_fused01_kernel<F32, TERMS>;
-    static bool configured[16] = {};
-    if (!configured[c->device & 15]) {
-        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedGeom::smem_bytes));
-        configured[c->device & 15] = true;
-    }
+    static std::atomic<unsigned long long> configured{0};
+    SVGF_CUDA(c, configure_smem_once(configured, c->device, kern, FusedGeom::smem_bytes));
     const dim3 grid((c->W + kFzW - 1) / kFzW, (c->H + kFzH - 1) / kFzH);
     kern<<<grid, kFzThreads, FusedGeom::smem_bytes, s>>>(t, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in, (CT *)out,
                                                          (CT *)hist_colour);

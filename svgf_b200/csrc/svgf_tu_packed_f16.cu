@@ -10,14 +10,11 @@ svgf_status launch_atrous_packed(svgf_ctx *c, AtrousTiledArgs a, int guide_slot,
     using CT = typename ColourPlane<F32>::texel;
     using G = PackedGeom<STEP>;
     auto kern = atrous_packed_kernel<F32, STEP, TERMS, R, PREF, HC>;
-    static bool configured[16] = {};
-    if (!configured[c->device & 15]) {
-        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
-        configured[c->device & 15] = true;
-    }
+    static std::atomic<unsigned long long> configured{0};
+    SVGF_CUDA(c, configure_smem_once(configured, c->device, kern, G::smem_bytes));
     const dim3 grid((c->W + kTileW - 1) / kTileW, ((c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP)) * STEP);
     kern<<<grid, kPkPairs * (G::tile_rows / R), G::smem_bytes, s>>>(a, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in, (CT *)out,
-                                                 (CT *)hist_colour);
+                                                 (CT *)hist_colour, LatticeColour{nullptr, nullptr, nullptr}, LatticeNormals{nullptr, nullptr}, 0);
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
     return SVGF_OK;
@@ -50,7 +47,6 @@ svgf_status atrous_packed_f16(svgf_ctx *c, int terms, int rows, const AtrousTile
         return terms == 3 ? dispatch_atrous_packed<false, 3, kPkRows, true>(c, a, guide_slot, in, out, hist_colour, s) : SVGF_UNSUPPORTED;
     switch (terms) {
         case 3: return dispatch_atrous_packed<false, 3, kPkRows>(c, a, guide_slot, in, out, hist_colour, s);
-        case 4: return dispatch_atrous_packed<false, 4, kPkRows>(c, a, guide_slot, in, out, hist_colour, s);
         case 5: return dispatch_atrous_packed<false, 5, kPkRows>(c, a, guide_slot, in, out, hist_colour, s);
     }
     return SVGF_UNSUPPORTED;

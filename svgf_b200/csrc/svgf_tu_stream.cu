@@ -10,12 +10,9 @@ svgf_status launch_atrous_stream(svgf_ctx *c, const AtrousTiledArgs &t, int guid
     using CT = typename ColourPlane<F32>::texel;
     using G = StreamGeom<STEP>;
     auto kern = atrous_stream_kernel<F32, STEP, TERMS>;
-    static bool configured[16] = {};
+    static std::atomic<unsigned long long> configured{0};
     const size_t smem = G::smem_bytes;
-    if (!configured[c->device & 15]) {
-        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[c->device & 15] = true;
-    }
+    SVGF_CUDA(c, configure_smem_once(configured, c->device, kern, smem));
     AtrousStreamArgs a;
     a.t = t;
     a.n_strips = (c->W + kStripW - 1) / kStripW;

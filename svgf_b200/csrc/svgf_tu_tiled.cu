@@ -10,14 +10,14 @@ svgf_status launch_atrous_tiled(svgf_ctx *c, AtrousTiledArgs a, int guide_slot, 
     using CT = typename ColourPlane<F32>::texel;
     using G = TileGeom<F32, STEP, RG>;
     auto kern = atrous_tiled_kernel<F32, STEP, RG, TERMS>;
-    static int ctas_per_sm[16] = {};   // per device, 0 = not configured yet
-    int &cps = ctas_per_sm[c->device & 15];
+    static std::atomic<unsigned long long> configured{0};
+    static std::atomic<int> ctas_per_sm{0};   // a property of the kernel and of sm_100a, identical on every device
+    SVGF_CUDA(c, configure_smem_once(configured, c->device, kern, G::smem_bytes));
+    int cps = ctas_per_sm.load(std::memory_order_relaxed);
     if (cps == 0) {
-        SVGF_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem_bytes));
-        int n = 0;
-        SVGF_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, G::threads, G::smem_bytes));
-        if (n < 1) return SVGF_UNSUPPORTED;
-        cps = n;
+        SVGF_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, kern, G::threads, G::smem_bytes));
+        if (cps < 1) return SVGF_UNSUPPORTED;
+        ctas_per_sm.store(cps, std::memory_order_relaxed);
     }
     a.tiles_x = (c->W + kTileW - 1) / kTileW;
     a.tiles_y = ((c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP)) * STEP;

@@ -201,6 +201,12 @@ class SvgfFilter:
         self._check(self.lib.svgf_profile_end(self._ctx, C.byref(ms), C.byref(n)), "svgf_profile_end")
         return {"temporal_ms": ms[0], "variance_ms": ms[1], "atrous_ms": ms[2], "frames": n.value}
 
+    def last_dispatch(self):
+        """Kernel family (svgf_dispatch_family) that ran each a-trous level of the most recent Filter / WaveletFilter call."""
+        fam = (C.c_int32 * 16)()
+        n = self.lib.svgf_last_dispatch(self._ctx, fam, 16)
+        return [int(fam[i]) for i in range(min(n, 16))]
+
     def invalidate_guide(self):
         self.lib.svgf_invalidate_guide(self._ctx)
 

@@ -48,7 +48,7 @@ def test_two_levels_fused_equal_two_launches_and_the_oracle(storage, size):
     f = SvgfFilter(W, H, storage=storage)
     load_state_from_oracle(f, of)
     l0 = f.launches
-    ref, ref_h = _levels(f, 2, 0)
+    ref, ref_h = _levels(f, 2, _lib.SVGF_FLAG_NO_STAGED_LEVELS)    # two single-level launches of the packed kernel
     load_state_from_oracle(f, of)
     l1 = f.launches
     got, got_h = _levels(f, 2, _lib.SVGF_FLAG_FUSE_LEVELS_01)
@@ -77,6 +77,7 @@ def test_sequence_through_svgf_frame_is_bit_identical_fused_and_unfused(storage,
     W, H, N = 1280, 720, 5
     a, b = SvgfFilter(W, H, storage=storage), SvgfFilter(W, H, storage=storage)
     a.SpatialFilterSteps = b.SpatialFilterSteps = levels
+    a.params.flags = _lib.SVGF_FLAG_NO_STAGED_LEVELS
     b.params.flags = _lib.SVGF_FLAG_FUSE_LEVELS_01
     a.Reset(); b.Reset()
     for t in range(N):

@@ -211,12 +211,27 @@ def test_argument_validation_through_the_abi():
 
 
 @pytest.mark.parametrize("variant", ["stream", "bulk"])
-def test_atrous_kernel_variants_meet_the_same_bar(variant):
-    # SVGF_ATROUS_VARIANT is read once per process: run the a-trous parity tests of this file in a child process
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, SVGF_ATROUS_VARIANT=variant)
-    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-m", "gpu", "-q", "-x", "-k", "atrous_single_level or atrous_cascade",
-                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+@pytest.mark.parametrize("storage", ["f16", "f32"])
+@pytest.mark.parametrize("level", [0, 1, 2, 3, 4])
+def test_atrous_kernel_variants_meet_the_same_bar(variant, storage, level):
+    # the A/B kernel families (svgf_params.flags) against the oracle, one level at a time like test_atrous_single_level
+    flag = {"stream": _lib.SVGF_FLAG_ATROUS_STREAM, "bulk": _lib.SVGF_FLAG_ATROUS_BULK}[variant]
+    fam = {"stream": _lib.SVGF_FAMILY_STREAM, "bulk": _lib.SVGF_FAMILY_BULK}[variant]
+    for W, H in [(130, 67), (258, 129)]:
+        of, f = make_pair(W, H, storage, seed=W * 13 + H + level)
+        _atrous_inputs(of, f, np.random.default_rng(9 + level), smooth=False)
+        P = of.PingPongInx
+        g = of.gbuf(P)
+        out = np.zeros_like(of.FilterBuffer[0])
+        hc = of.RenderBuffer[P].copy()
+        assert oracle().svgf_oracle_atrous_level(C.byref(of.params), W, H, of.storage, C.byref(g), of.FilterBuffer[0].ctypes.data,
+                                                 out.ctypes.data, hc.ctypes.data, level) == 0
+        f.params.flags = flag
+        res = C.c_void_p()
+        gs = f.Framebuffer[P].as_struct()
+        st = f.lib.svgf_atrous(f._ctx, C.byref(f.params), C.byref(gs), C.c_void_p(f.FilterBuffer[0].data_ptr()),
+                               C.c_void_p(f.FilterBuffer[1].data_ptr()), C.c_void_p(f.RenderBuffer[P].data_ptr()), level, 1,
+                               C.byref(res), f._stream())
+        assert st == 0 and f.last_dispatch()[level] == fam
+        assert_close(npy(f.FilterBuffer[1]), out, storage, f"{variant} a-trous level {level} {W}x{H}")
+        assert_close(npy(f.RenderBuffer[P]), hc, storage, f"{variant} colour history after level {level}")
