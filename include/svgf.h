@@ -207,6 +207,15 @@ svgf_status svgf_atrous(svgf_ctx *ctx, const svgf_params *params, const svgf_gbu
 svgf_status svgf_frame(svgf_ctx *ctx, const svgf_params *params, const svgf_gbuffer gbuf[2],
                        const svgf_frame_buffers *bufs, void *stream);
 
+/* Replaces application::TAA() (src/App.cu:516-522) -> filter::TAAFilterKernel (src/Filter.cuh:288-357): temporal
+ * anti-aliasing of the filtered frame against the previous resolve (3x3 neighbourhood clamp in PAL-YUV, :267-285) and
+ * sRGB encoding (:145-148); the output alpha is 1.  `filtered` is svgf_frame's result (filter[0]); `taa_history` is the
+ * PREVIOUS call's taa_out (all zeros before the first frame: alpha 0 makes the blend take none of the current texel, as
+ * in the reference); `taa_out` receives this frame's display image.  The reference passes one plane in both roles and
+ * reads texels other threads may already have overwritten (src/Filter.cuh:299 vs :355); here the two must be distinct
+ * planes that the caller swaps every frame (snapshot semantics). */
+svgf_status svgf_taa(svgf_ctx *ctx, const void *filtered, const void *taa_history, void *taa_out, void *stream);
+
 /* The context caches a compact "guide" plane (depth, depth derivative, normal, mesh id: 22 B/px) per
  * G-buffer, keyed by the three plane pointers and pitches of the svgf_gbuffer: svgf_temporal / svgf_frame build it for the current
  * G-buffer, the following svgf_variance / svgf_atrous calls naming the same G-buffer reuse it, and the next

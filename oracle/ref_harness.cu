@@ -212,6 +212,14 @@ int svgf_ref_atrous_level(svgf_ref_ctx *c, const svgf_ref_params *p, int level) 
     return (int)cudaGetLastError();
 }
 
+// application::TAA, src/App.cu:516-522: FilterBuffer[0] -> FilterBuffer[1], which is also read as the history (D13: racy
+// unless the history is a fixed point of the kernel - tests/test_taa.py iterates it to one)
+int svgf_ref_taa(svgf_ref_ctx *c) {
+    dim3 block(16, 16), grid(c->W / 16 + 1, c->H / 16 + 1);
+    filter::TAAFilterKernel<<<grid, block>>>(c->filt[0], c->filt[1], c->W, c->H);
+    return (int)cudaGetLastError();
+}
+
 // Render()'s filter stages (src/App.cu:552-556) + EndFrame's flip (src/App.cu:374)
 int svgf_ref_frame(svgf_ref_ctx *c, const svgf_ref_params *p, int flip) {
     int e;

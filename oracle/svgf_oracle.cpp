@@ -393,6 +393,75 @@ void atrous(const svgf_params &P, int W, int H, const GBuf &G, const void *in, v
     }
 }
 
+// ---- A.6 TAA + sRGB resolve: TAAFilterKernel, src/Filter.cuh:288-357 (encodePalYuv / decodePalYuv :267-285, ToSRGB
+// :145-148, textureSample :116-141 which returns the floor texel - the bilinear part is dead code behind `return c00`).
+// D13: the reference reads its history from the plane it is writing (`Output`, :299 vs :355; another thread may already
+// have overwritten the texel) - here the history is a separate plane (snapshot semantics, like D3).
+inline V3 encode_pal_yuv(V3 rgb) {                                                   // :267-275
+    rgb = {powf(rgb.x, 2.0f), powf(rgb.y, 2.0f), powf(rgb.z, 2.0f)};                 // glm::pow(vec3, vec3(2.0))
+    return {dot3(rgb, {0.299f, 0.587f, 0.114f}), dot3(rgb, {-0.14713f, -0.28886f, 0.436f}), dot3(rgb, {0.615f, -0.51499f, -0.10001f})};
+}
+inline V3 decode_pal_yuv(V3 yuv) {                                                   // :277-285
+    const V3 rgb = {dot3(yuv, {1.0f, 0.0f, 1.13983f}), dot3(yuv, {1.0f, -0.39465f, -0.58060f}), dot3(yuv, {1.0f, 2.03211f, 0.0f})};
+    return {powf(rgb.x, 0.5f), powf(rgb.y, 0.5f), powf(rgb.z, 0.5f)};                // glm::pow(vec3, vec3(1.0 / 2.0))
+}
+inline float to_srgb(float c) {                                                      // :145-148
+    return (c <= 0.0031308f) ? 12.92f * c : (1 + 0.055f) * powf(c, 1 / 2.4f) - 0.055f;
+}
+inline V3 min3(V3 a, V3 b) { return {glm_min(a.x, b.x), glm_min(a.y, b.y), glm_min(a.z, b.z)}; }
+inline V3 max3(V3 a, V3 b) { return {glm_max(a.x, b.x), glm_max(a.y, b.y), glm_max(a.z, b.z)}; }
+// glm::mix(vec3, vec3, double 0.5): evaluated in double, rounded to float once (submodules/glm/glm/detail/func_common.inl)
+inline float mix_half_d(float x, float y) { return (float)((double)x * (1.0 - 0.5) + (double)y * 0.5); }
+
+template <bool F32>
+void taa(int W, int H, const void *filtered, const void *history, void *out) {
+    const float inv_w = 1.0f / float(W), inv_h = 1.0f / float(H);                    // :294 (and `off`, :305)
+    // textureSample :116-131: x = uv.x * (Width - 1); x0 = floor(x); clamp; imageLoad (value clamp [0,1])
+    auto sample = [&](const void *plane, float u, float v) -> V4 {
+        const float x = u * (float)(W - 1), y = v * (float)(H - 1);
+        int x0 = (int)floorf(x), y0 = (int)floorf(y);
+        x0 = x0 < 0 ? 0 : (x0 > W - 1 ? W - 1 : x0);
+        y0 = y0 < 0 ? 0 : (y0 > H - 1 ? H - 1 : y0);
+        return Colour<F32>::ld01(plane, (size_t)y0 * W + x0);
+    };
+#pragma omp parallel for schedule(static) num_threads(g_threads > 0 ? g_threads : omp_get_max_threads())
+    for (int py = 0; py < H; py++) {
+        for (int px = 0; px < W; px++) {
+            const float u = (float)px * inv_w, v = (float)py * inv_h;                // :296
+            const V4 last = sample(history, u, v);                                   // :299
+            V3 aa = {last.x, last.y, last.z};
+            const float mix_rate = (float)fmin((double)last.w, 0.5);                 // :302
+            const V4 s0 = sample(filtered, u, v);                                    // :306
+            V3 in[9];
+            in[0] = {s0.x, s0.y, s0.z};
+            aa = {mixf(aa.x * aa.x, in[0].x * in[0].x, mix_rate), mixf(aa.y * aa.y, in[0].y * in[0].y, mix_rate),
+                  mixf(aa.z * aa.z, in[0].z * in[0].z, mix_rate)};                   // :308
+            aa = {sqrtf(aa.x), sqrtf(aa.y), sqrtf(aa.z)};                            // :309
+            const float du[8] = {+inv_w, -inv_w, 0.0f, 0.0f, +inv_w, -inv_w, +inv_w, -inv_w};   // :311-318
+            const float dv[8] = {0.0f, 0.0f, +inv_h, -inv_h, +inv_h, +inv_h, -inv_h, -inv_h};
+            for (int k = 0; k < 8; k++) {
+                const V4 t = sample(filtered, u + du[k], v + dv[k]);
+                in[k + 1] = {t.x, t.y, t.z};
+            }
+            aa = encode_pal_yuv(aa);                                                 // :320
+            for (int k = 0; k < 9; k++) in[k] = encode_pal_yuv(in[k]);               // :321-329
+            V3 mn = min3(min3(min3(in[0], in[1]), min3(in[2], in[3])), in[4]);       // :331
+            V3 mx = max3(max3(max3(in[0], in[1]), max3(in[2], in[3])), in[4]);       // :332
+            const V3 mn2 = min3(min3(min3(in[5], in[6]), min3(in[7], in[8])), mn);
+            const V3 mx2 = max3(max3(max3(in[5], in[6]), max3(in[7], in[8])), mx);
+            mn = {mix_half_d(mn.x, mn2.x), mix_half_d(mn.y, mn2.y), mix_half_d(mn.z, mn2.z)};   // :333-334
+            mx = {mix_half_d(mx.x, mx2.x), mix_half_d(mx.y, mx2.y), mix_half_d(mx.z, mx2.z)};   // :335-336
+            aa = {glm_min(glm_max(aa.x, mn.x), mx.x), glm_min(glm_max(aa.y, mn.y), mx.y), glm_min(glm_max(aa.z, mn.z), mx.z)};   // :339
+            // :341-346 update mixRate, which is never stored (the output alpha is the constant 1, :350,:353)
+            aa = decode_pal_yuv(aa);                                                 // :348
+            V4 frag = {aa.x, aa.y, aa.z, 1.0f};
+            if (aa.x != aa.x || aa.y != aa.y || aa.z != aa.z) frag = {0.0f, 0.0f, 0.0f, 0.0f};   // :351 IsFinite == !isnan (src/Common.cuh:85-93)
+            frag = {to_srgb(frag.x), to_srgb(frag.y), to_srgb(frag.z), 1.0f};        // :353
+            Colour<F32>::st01(out, (size_t)py * W + px, frag);                       // :355 imageStore
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -469,6 +538,15 @@ int svgf_oracle_frame(const svgf_params *p, int W, int H, int storage, const svg
     }
     if (p->atrous_iterations % 2 != 0)  // src/App.cu:510-513
         std::memcpy(b->filter[0], b->filter[1], n * (storage == SVGF_STORE_F32 ? 16 : 8));
+    return SVGF_OK;
+}
+
+// src/Filter.cuh:288-357, launched at src/App.cu:516-522.  `history` is the previous call's output (D13); must not alias `out`.
+int svgf_oracle_taa(int W, int H, int storage, const void *filtered, const void *history, void *out) {
+    if (W <= 0 || H <= 0 || !filtered || !history || !out || history == out || filtered == out) return SVGF_INVALID_ARG;
+    if (storage == SVGF_STORE_F32) taa<true>(W, H, filtered, history, out);
+    else if (storage == SVGF_STORE_F16) taa<false>(W, H, filtered, history, out);
+    else return SVGF_INVALID_ARG;
     return SVGF_OK;
 }
 

@@ -73,6 +73,7 @@ ABI = [
                               C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),
     ("svgf_frame", C.c_int, [C.c_void_p, C.POINTER(SvgfParams), C.POINTER(SvgfGBuffer * 2), C.POINTER(SvgfFrameBuffers),
                              C.c_void_p]),
+    ("svgf_taa", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("svgf_invalidate_guide", None, [C.c_void_p]),
     ("svgf_profile_begin", C.c_int, [C.c_void_p]),
     ("svgf_profile_end", C.c_int, [C.c_void_p, C.POINTER(C.c_double * 3), C.POINTER(C.c_int)]),

@@ -10,6 +10,7 @@
 #include "../../include/svgf.h"
 #include "svgf_ctx.h"
 #include "svgf_kernels_basic.cuh"
+#include "svgf_kernels_taa.cuh"
 #include <cstdlib>
 
 using namespace svgf;
@@ -434,6 +435,8 @@ svgf_status svgf_create(svgf_ctx **out, int device, int width, int height, svgf_
     if (e == cudaSuccess) e = cudaMalloc(&c->worklist, n * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&c->work_counter, 2 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(c->work_counter, 0, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&c->tile_counters, 8 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(c->tile_counters, 0, 8 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(c->hist_shadow, 0, n);
     if (e != cudaSuccess) { svgf_destroy(c); return SVGF_CUDA_ERROR; }
     *out = c;
@@ -446,6 +449,7 @@ void svgf_destroy(svgf_ctx *c) {
     cudaFree(c->hist_shadow);
     cudaFree(c->worklist);
     cudaFree(c->work_counter);
+    cudaFree(c->tile_counters);
     cudaFree(c->var_blur);
     for (int k = 0; k < 2; k++) { cudaFree(c->guide[k].n); cudaFree(c->guide[k].dz); cudaFree(c->guide[k].mid); cudaFree(c->guide[k].seg); }
     lattice_destroy(c);
@@ -606,6 +610,20 @@ svgf_status svgf_frame(svgf_ctx *c, const svgf_params *p, const svgf_gbuffer gbu
     prof_mark(c, 3, s);
     if (c->profiling && c->prof_frames < svgf_ctx::kMaxProf) c->prof_frames++;
     return (result == b->filter[0]) ? SVGF_OK : SVGF_CUDA_ERROR;  // invariant of the rotation above
+}
+
+svgf_status svgf_taa(svgf_ctx *c, const void *filtered, const void *taa_history, void *taa_out, void *stream) {
+    if (!c || !filtered || !taa_history || !taa_out || taa_history == taa_out || filtered == taa_out) return SVGF_INVALID_ARG;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return SVGF_CUDA_ERROR;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->storage == SVGF_STORE_F32)
+        taa_kernel<true><<<grid_for(c), 256, 0, s>>>(c->W, c->H, (const float4 *)filtered, (const float4 *)taa_history, (float4 *)taa_out);
+    else
+        taa_kernel<false><<<grid_for(c), 256, 0, s>>>(c->W, c->H, (const uint2 *)filtered, (const uint2 *)taa_history, (uint2 *)taa_out);
+    c->launches++;
+    SVGF_CUDA(c, cudaGetLastError());
+    return SVGF_OK;
 }
 
 // ---- stage profiling -----------------------------------------------------------------------------------------

@@ -1,0 +1,86 @@
+// svgf_kernels_taa.cuh — temporal anti-aliasing + sRGB resolve, the step right after the a-trous levels:
+// reference filter::TAAFilterKernel (src/Filter.cuh:288-357), launched by application::TAA() (src/App.cu:516-522).
+//
+// What the reference kernel does per pixel (x, y):
+//   * every "texture sample" is textureSample (:116-131), which returns the FLOOR texel of uv * (size - 1) (the bilinear
+//     part is dead code), with uv = (x, y) / size: for almost every pixel that is texel (x - 1, y - 1) - the resolve shifts
+//     the image by one pixel.  Reproduced by evaluating the same float expressions, not by assuming the shift;
+//   * history (previous output, sRGB-encoded, alpha 1) and the current texel are blended in squared space with rate
+//     min(alpha, 0.5), the result is clamped in PAL-YUV to the box of the 3x3 neighbourhood (plus-shaped box, then averaged
+//     with the full box), decoded, NaN -> 0, sRGB-encoded (:145-148) and stored with alpha 1.  The mix-rate update of
+//     :341-346 never reaches memory (the stored alpha is the constant 1) and is not evaluated.
+// D13: the reference reads the history from the very plane it writes (another thread may have overwritten the texel,
+// and application::TAA passes FilterBuffer[1], which the a-trous ping-pong has just used as scratch).  Here the history is
+// a separate, caller-owned plane: the previous call's output (snapshot semantics, like the history-length plane, D3).
+//
+// Pure streaming pass: 8 B in + 8 B history + 8 B out per pixel (fp16 storage); the nine neighbourhood texels of a pixel
+// are shared with its neighbours through L1.  pow(x, 2) = x * x, pow(x, 0.5) = sqrt, pow(x, 1/2.4) = ex2(lg2(x) / 2.4):
+// MUFU approximations (<= 2^-21 relative) - the result is rounded to the storage format and compared at the parity bar.
+#pragma once
+#include "svgf_device.cuh"
+
+namespace svgf {
+
+__device__ __forceinline__ float3 taa_encode_pal_yuv(float3 c) {                     // :267-275
+    const float r = c.x * c.x, g = c.y * c.y, b = c.z * c.z;
+    return make_float3((r * 0.299f + g * 0.587f) + b * 0.114f, (r * -0.14713f + g * -0.28886f) + b * 0.436f,
+                       (r * 0.615f + g * -0.51499f) + b * -0.10001f);
+}
+__device__ __forceinline__ float taa_sqrt(float x) {   // pow(x, 0.5): NaN for x < 0, +0 for -0
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y + 0.0f;
+}
+__device__ __forceinline__ float taa_to_srgb(float c) {                             // :145-148
+    const float hi = 1.055f * fast_exp2(fast_log2(fmaxf(c, 1e-30f)) * (1.0f / 2.4f)) - 0.055f;
+    return (c <= 0.0031308f) ? 12.92f * c : hi;
+}
+// floor texel of textureSample (:116-131) along one axis: uv * (size - 1), floor, clamp
+__device__ __forceinline__ int taa_texel(float uv, int size) {
+    const int t = __float2int_rd(uv * (float)(size - 1));
+    return min(max(t, 0), size - 1);
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(256)
+taa_kernel(int W, int H, const typename ColourPlane<F32>::texel *__restrict__ filtered,
+           const typename ColourPlane<F32>::texel *__restrict__ history, typename ColourPlane<F32>::texel *__restrict__ out) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const float inv_w = 1.0f / (float)W, inv_h = 1.0f / (float)H;
+    const float u = (float)x * inv_w, v = (float)y * inv_h;                          // :296
+    const int xs[3] = {taa_texel(u - inv_w, W), taa_texel(u, W), taa_texel(u + inv_w, W)};
+    const int ys[3] = {taa_texel(v - inv_h, H), taa_texel(v, H), taa_texel(v + inv_h, H)};
+    auto load = [&](const typename ColourPlane<F32>::texel *p, int ix, int iy) {
+        return clamp01(ColourPlane<F32>::decode(__ldg(p + (size_t)ys[iy] * W + xs[ix])));   // imageLoad :78-83
+    };
+    const float4 last = load(history, 1, 1);                                         // :299
+    const float4 c0 = load(filtered, 1, 1);                                          // :306
+    const float rate = fminf(last.w, 0.5f);                                          // :302
+    float3 aa = make_float3(mix_rn(last.x * last.x, c0.x * c0.x, rate), mix_rn(last.y * last.y, c0.y * c0.y, rate),
+                            mix_rn(last.z * last.z, c0.z * c0.z, rate));             // :308
+    aa = taa_encode_pal_yuv(make_float3(taa_sqrt(aa.x), taa_sqrt(aa.y), taa_sqrt(aa.z)));   // :309,:320
+    // plus-shaped box (in0..in4), then the diagonal texels (in5..in8) folded in: :331-336
+    const float3 e0 = taa_encode_pal_yuv(make_float3(c0.x, c0.y, c0.z));
+    float3 mn = e0, mx = e0;
+    auto fold = [&](int ix, int iy, float3 &lo, float3 &hi) {
+        const float4 c = load(filtered, ix, iy);
+        const float3 e = taa_encode_pal_yuv(make_float3(c.x, c.y, c.z));
+        lo = make_float3(fminf(lo.x, e.x), fminf(lo.y, e.y), fminf(lo.z, e.z));
+        hi = make_float3(fmaxf(hi.x, e.x), fmaxf(hi.y, e.y), fmaxf(hi.z, e.z));
+    };
+    fold(2, 1, mn, mx); fold(0, 1, mn, mx); fold(1, 2, mn, mx); fold(1, 0, mn, mx);
+    float3 mn2 = mn, mx2 = mx;
+    fold(2, 2, mn2, mx2); fold(0, 2, mn2, mx2); fold(2, 0, mn2, mx2); fold(0, 0, mn2, mx2);
+    mn = make_float3(0.5f * mn.x + 0.5f * mn2.x, 0.5f * mn.y + 0.5f * mn2.y, 0.5f * mn.z + 0.5f * mn2.z);   // exact halves: one rounding, like the reference's FP64 mix
+    mx = make_float3(0.5f * mx.x + 0.5f * mx2.x, 0.5f * mx.y + 0.5f * mx2.y, 0.5f * mx.z + 0.5f * mx2.z);
+    aa = make_float3(fminf(fmaxf(aa.x, mn.x), mx.x), fminf(fmaxf(aa.y, mn.y), mx.y), fminf(fmaxf(aa.z, mn.z), mx.z));   // :339
+    // decodePalYuv :277-285
+    float3 rgb = make_float3(aa.x + aa.z * 1.13983f, (aa.x + aa.y * -0.39465f) + aa.z * -0.58060f, aa.x + aa.y * 2.03211f);
+    rgb = make_float3(taa_sqrt(rgb.x), taa_sqrt(rgb.y), taa_sqrt(rgb.z));
+    if (rgb.x != rgb.x || rgb.y != rgb.y || rgb.z != rgb.z) rgb = make_float3(0.f, 0.f, 0.f);   // :351
+    const float4 o = make_float4(taa_to_srgb(rgb.x), taa_to_srgb(rgb.y), taa_to_srgb(rgb.z), 1.0f);   // :353
+    out[(size_t)y * W + x] = ColourPlane<F32>::encode(clamp01(o));                   // :355 imageStore
+}
+
+}  // namespace svgf

@@ -77,6 +77,7 @@ class SvgfFilter:
         self.MomentsBuffer = [torch.zeros(H, W, 2, dtype=cdt, device=dev) for _ in range(2)]
         self.FilterBuffer = [torch.zeros(H, W, 4, dtype=cdt, device=dev) for _ in range(2)]
         self.HistoryLengthBuffer = torch.zeros(H, W, dtype=torch.uint8, device=dev)
+        self.TAABuffer = None     # allocated by the first TAA() call
         self.PingPongInx = 0
         # tunables, reference src/App.h:109-114 (SpatialFilterSteps is 3 there; BASELINE.json measures 5)
         self.params = _lib.default_params()
@@ -186,6 +187,17 @@ class SvgfFilter:
         b = self._bufs()
         g = (SvgfGBuffer * 2)(self.Framebuffer[0].as_struct(), self.Framebuffer[1].as_struct())
         self._check(self.lib.svgf_frame(self._ctx, C.byref(self.params), C.byref(g), C.byref(b), self._stream()), "svgf_frame")
+
+    def TAA(self):
+        """application::TAA(), reference src/App.cu:516-522: FilterBuffer[0] -> TAABuffer[PingPongInx], history =
+        TAABuffer[1 - PingPongInx] (the previous frame's resolve).  The reference resolves into FilterBuffer[1] and reads its
+        history from that same plane while writing it (D13); two planes swapped per frame make that read well-defined."""
+        if self.TAABuffer is None:
+            self.TAABuffer = [torch.zeros_like(self.FilterBuffer[0]) for _ in range(2)]
+        P = self.PingPongInx
+        st = self.lib.svgf_taa(self._ctx, _ptr(self.FilterBuffer[0]), _ptr(self.TAABuffer[1 - P]), _ptr(self.TAABuffer[P]), self._stream())
+        self._check(st, "svgf_taa")
+        return self.TAABuffer[P]
 
     def EndFrame(self):
         """application::EndFrame()'s filter-relevant line, reference src/App.cu:374."""

@@ -32,6 +32,7 @@ def oracle():
         o.svgf_oracle_variance.argtypes = [P, C.c_int, C.c_int, C.c_int, G, v, v, v, v]
         o.svgf_oracle_atrous_level.argtypes = [P, C.c_int, C.c_int, C.c_int, G, v, v, v, C.c_int]
         o.svgf_oracle_frame.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(SvgfGBuffer * 2), C.POINTER(SvgfFrameBuffers)]
+        o.svgf_oracle_taa.argtypes = [C.c_int, C.c_int, C.c_int, v, v, v]
         _o = o
     return _o
 
@@ -128,8 +129,26 @@ class OracleFilter:
         _chk(oracle().svgf_oracle_frame(C.byref(self.params), self.Width, self.Height, self.storage, C.byref(g), C.byref(b)),
              "oracle frame")
 
+    def TAA(self):
+        """svgf_oracle_taa: FilterBuffer[0] -> TAABuffer[PingPongInx], history = TAABuffer[1 - PingPongInx] (snapshot, D13)."""
+        if getattr(self, "TAABuffer", None) is None:
+            self.TAABuffer = [np.zeros_like(self.FilterBuffer[0]) for _ in range(2)]
+        P = self.PingPongInx
+        _chk(oracle().svgf_oracle_taa(self.Width, self.Height, self.storage, self.FilterBuffer[0].ctypes.data,
+                                      self.TAABuffer[1 - P].ctypes.data, self.TAABuffer[P].ctypes.data), "oracle taa")
+        return self.TAABuffer[P]
+
     def EndFrame(self):
         self.PingPongInx = 1 - self.PingPongInx
+
+
+def oracle_taa(filtered, history, storage):
+    """One TAA + sRGB resolve by the oracle on numpy planes; returns the output plane."""
+    H, W = filtered.shape[:2]
+    out = np.zeros_like(filtered)
+    _chk(oracle().svgf_oracle_taa(W, H, 0 if storage == "f16" else 1, np.ascontiguousarray(filtered).ctypes.data,
+                                  np.ascontiguousarray(history).ctypes.data, out.ctypes.data), "oracle taa")
+    return out
 
 
 # ---- the reference's own kernels (GPU only) ---------------------------------------------------------------
@@ -163,6 +182,8 @@ def ref():
         for n in ("svgf_ref_temporal", "svgf_ref_variance", "svgf_ref_wavelet"):
             getattr(r, n).argtypes = [v, RP]
         r.svgf_ref_atrous_level.argtypes = [v, RP, C.c_int]
+        if hasattr(r, "svgf_ref_taa"):
+            r.svgf_ref_taa.argtypes = [v]
         r.svgf_ref_frame.argtypes = [v, RP, C.c_int]
         r.svgf_ref_frame_host.argtypes = [v, RP, v, v, v, v, v, v]
         r.svgf_ref_time_frames.argtypes = [v, RP, C.c_int, C.POINTER(C.c_float)]

@@ -26,7 +26,14 @@ METRICS = [
     "smsp__average_warp_latency_issue_stalled_mio_throttle.ratio", "smsp__average_warp_latency_issue_stalled_barrier.ratio",
     "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio", "smsp__average_warp_latency_issue_stalled_wait.ratio",
     "smsp__average_warp_latency_issue_stalled_not_selected.ratio", "smsp__average_warp_latency_issue_stalled_dispatch_stall.ratio",
-    "smsp__average_warp_latency_issue_stalled_lg_throttle.ratio",
+    "smsp__average_warp_latency_issue_stalled_lg_throttle.ratio", "smsp__average_warp_latency_issue_stalled_no_instruction.ratio",
+    "smsp__average_warp_latency_issue_stalled_sleeping.ratio", "smsp__average_warp_latency_issue_stalled_membar.ratio",
+    "smsp__average_warp_latency_issue_stalled_selected.ratio", "smsp__average_warp_latency_issue_stalled_branch_resolving.ratio",
+    "smsp__average_warp_latency_issue_stalled_imc_miss.ratio", "smsp__average_warp_latency_issue_stalled_drain.ratio",
+    "smsp__average_warp_latency_issue_stalled_tex_throttle.ratio",
+    "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum", "l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_l1tex2xbar_write_bytes.sum", "sm__ctas_launched.sum",
+    "smsp__cycles_active.avg", "sm__cycles_active.avg", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
