@@ -9,7 +9,8 @@
  * Conventions
  *  - All image pointers are caller-owned DEVICE memory, row-major, dense (`y*W + x`) for the colour /
  *    moments / history planes exactly like the reference's `buffer`s (src/App.cu:763-773); G-buffer planes
- *    carry a row pitch in bytes (0 = dense) because they originate from GL attachments.
+ *    are pitch-linear memory (row pitch in bytes, 0 = dense) or the reference's own texture objects over the GL
+ *    attachments (svgf_gbuffer below).
  *  - Texel formats are the reference's (src/App.cu:746-752, resources/shaders/GBuffer.frag:62-87):
  *      position_id  : float4  world xyz, w = primitive index            (never read by the filter; may be NULL)
  *      normal_mat   : ushort4 fp16 bit patterns: unit normal xyz, w = material index
@@ -94,8 +95,9 @@ typedef enum svgf_variance_prefilter { SVGF_VARIANCE_PREFILTER_NONE = 0, SVGF_VA
  * levels run STAGED: the first level (packed kernel) writes its result as context-owned, pre-transformed "lattice planes"
  * (fp32, clamped, pixel-pair interleaved, luminance attached - exactly what the next level's imageLoad would have produced,
  * src/Filter.cuh:78-83), the following levels load their tiles from those with tensor-map TMA and only the last level
- * writes the storage format again.  Results are within parity tolerance of the level-by-level path, not bit-identical
- * (the uniform-normal shortcut folds the normal term into the exponent's constant there). */
+ * writes the storage format again.  Results are BIT-identical to the level-by-level path (same arithmetic in the same
+ * order; the intermediate planes hold exactly what a storage-format round trip would have produced); the flag exists for
+ * A/B timing and for the tests that pin that identity. */
 #define SVGF_FLAG_NO_STAGED_LEVELS 32u
 /* A/B variants of the a-trous level, both measured slower than the default: the persistent bulk-copy
  * (cp.async.bulk) scalar kernel and the warp-specialised streaming kernel. */
@@ -138,8 +140,16 @@ typedef struct svgf_params {
     uint32_t flags;              /* SVGF_FLAG_* */
 } svgf_params;
 
-/* One G-buffer = the reference's `cudaFramebuffer` (src/App.h:41-44; attachment order src/App.h:33-39),
- * as pitch-linear device memory instead of cudaArray texture objects (TMA needs linear memory). */
+/* One G-buffer = the reference's `cudaFramebuffer` (src/App.h:41-44; attachment order src/App.h:33-39).  Each plane is either
+ *  - pitch-linear device memory (pitch in bytes, 0 = dense), or
+ *  - a cudaTextureObject_t, exactly what the reference passes (src/App.cu:473-475,485-486,504: CudaMappings[i]->TexObj,
+ *    created over the GL attachment's cudaArray by src/CudaUtil.h:68-99): store the handle in the pointer field
+ *    ((const void *)(uintptr_t)tex) and set the plane's pitch to SVGF_PITCH_TEXTURE.  The texture must be what CudaUtil.h
+ *    creates: element read mode, point filtering, un-normalised coordinates, channel format float4 (position, motion) /
+ *    ushort4 (normal, uv).  The kernels fetch it with tex2D at integer texel coordinates like src/Filter.cuh:182-207.
+ * The G-buffer is read once per frame (by the temporal pass, which compacts it into the context's guide planes), so
+ * texture-backed planes cost no extra pass and no copy. */
+#define SVGF_PITCH_TEXTURE ((size_t)-1)
 typedef struct svgf_gbuffer {
     const void *position_id;  size_t position_pitch;   /* float4;  may be NULL (not read by any filter kernel) */
     const void *normal_mat;   size_t normal_pitch;     /* ushort4 (fp16 bits) */

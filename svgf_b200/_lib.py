@@ -17,6 +17,7 @@ SVGF_FLAG_NO_STAGED_LEVELS, SVGF_FLAG_ATROUS_BULK, SVGF_FLAG_ATROUS_STREAM, SVGF
 # svgf_dispatch_family (svgf_last_dispatch)
 SVGF_FAMILY_BASIC, SVGF_FAMILY_PACKED, SVGF_FAMILY_PACKED_STAGED, SVGF_FAMILY_LATTICE = 1, 2, 3, 4
 SVGF_FAMILY_BULK, SVGF_FAMILY_STREAM, SVGF_FAMILY_FUSED01 = 5, 6, 7
+SVGF_PITCH_TEXTURE = C.c_size_t(-1).value
 SVGF_ABI_VERSION = 2
 
 
@@ -88,6 +89,10 @@ SYNTH_ABI = [
     ("svgf_synth_frame_host", C.c_int, [C.POINTER(SynthCfg)] + [C.c_void_p] * 5 + [C.c_int]),
     ("svgf_synth_rows_host", C.c_int, [C.POINTER(SynthCfg), C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int]),
     ("svgf_synth_frame_device", C.c_int, [C.POINTER(SynthCfg)] + [C.c_void_p] * 6),
+    ("svgf_synth_texgbuf_create", C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ("svgf_synth_texgbuf_destroy", None, [C.c_void_p]),
+    ("svgf_synth_texgbuf_upload", C.c_int, [C.c_void_p] * 5),
+    ("svgf_synth_texgbuf_objects", None, [C.c_void_p, C.POINTER(C.c_ulonglong * 3)]),
 ]
 
 _lib = None

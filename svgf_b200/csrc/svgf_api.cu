@@ -38,10 +38,13 @@ svgf_status check_params(const svgf_params *p) {
 svgf_status check_gbuf(const svgf_ctx *c, const svgf_gbuffer *g) {
     if (!g || !g->normal_mat || !g->uv_inst || !g->motion_depth) return SVGF_INVALID_ARG;
     const size_t W = (size_t)c->W;
-    if (g->normal_pitch && (g->normal_pitch < W * 8 || g->normal_pitch % 8)) return SVGF_INVALID_ARG;
-    if (g->uv_pitch && (g->uv_pitch < W * 8 || g->uv_pitch % 8)) return SVGF_INVALID_ARG;
-    if (g->motion_pitch && (g->motion_pitch < W * 16 || g->motion_pitch % 16)) return SVGF_INVALID_ARG;
-    if (((uintptr_t)g->normal_mat % 8) || ((uintptr_t)g->uv_inst % 8) || ((uintptr_t)g->motion_depth % 16)) return SVGF_INVALID_ARG;
+    // SVGF_PITCH_TEXTURE: the plane is a cudaTextureObject_t, nothing to check on the host
+    if (g->normal_pitch != SVGF_PITCH_TEXTURE && ((g->normal_pitch && (g->normal_pitch < W * 8 || g->normal_pitch % 8)) || ((uintptr_t)g->normal_mat % 8)))
+        return SVGF_INVALID_ARG;
+    if (g->uv_pitch != SVGF_PITCH_TEXTURE && ((g->uv_pitch && (g->uv_pitch < W * 8 || g->uv_pitch % 8)) || ((uintptr_t)g->uv_inst % 8)))
+        return SVGF_INVALID_ARG;
+    if (g->motion_pitch != SVGF_PITCH_TEXTURE && ((g->motion_pitch && (g->motion_pitch < W * 16 || g->motion_pitch % 16)) || ((uintptr_t)g->motion_depth % 16)))
+        return SVGF_INVALID_ARG;
     return SVGF_OK;
 }
 
@@ -53,6 +56,7 @@ GBufView view(const svgf_ctx *c, const svgf_gbuffer *g) {
     v.normal_pitch = g->normal_pitch ? g->normal_pitch : (size_t)c->W * 8;
     v.uv_pitch = g->uv_pitch ? g->uv_pitch : (size_t)c->W * 8;
     v.motion_pitch = g->motion_pitch ? g->motion_pitch : (size_t)c->W * 16;
+    v.tex = (g->normal_pitch == SVGF_PITCH_TEXTURE ? 1 : 0) | (g->uv_pitch == SVGF_PITCH_TEXTURE ? 2 : 0) | (g->motion_pitch == SVGF_PITCH_TEXTURE ? 4 : 0);
     return v;
 }
 
@@ -435,8 +439,6 @@ svgf_status svgf_create(svgf_ctx **out, int device, int width, int height, svgf_
     if (e == cudaSuccess) e = cudaMalloc(&c->worklist, n * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&c->work_counter, 2 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(c->work_counter, 0, 2 * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMalloc(&c->tile_counters, 8 * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(c->tile_counters, 0, 8 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(c->hist_shadow, 0, n);
     if (e != cudaSuccess) { svgf_destroy(c); return SVGF_CUDA_ERROR; }
     *out = c;
@@ -449,7 +451,6 @@ void svgf_destroy(svgf_ctx *c) {
     cudaFree(c->hist_shadow);
     cudaFree(c->worklist);
     cudaFree(c->work_counter);
-    cudaFree(c->tile_counters);
     cudaFree(c->var_blur);
     for (int k = 0; k < 2; k++) { cudaFree(c->guide[k].n); cudaFree(c->guide[k].dz); cudaFree(c->guide[k].mid); cudaFree(c->guide[k].seg); }
     lattice_destroy(c);

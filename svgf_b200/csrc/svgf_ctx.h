@@ -21,7 +21,6 @@ struct svgf_ctx {
     unsigned int *worklist = nullptr;     // indices of short-history pixels queued by the fused temporal pass
     unsigned int *work_counter = nullptr; // two counters used alternately: the sparse variance pass of frame t zeroes frame t+1's
     int work_parity = 0;
-    unsigned int *tile_counters = nullptr; // [8] dynamic tile scheduler of the persistent lattice levels, one counter per level
     float *var_blur = nullptr;            // 3x3-blurred variance of the current a-trous input (GAUSS3 prefilter), allocated on first use
     // identity of the G-buffer each guide plane was built from: the three plane pointers, their pitches and the caller's
     // generation counter (svgf_gbuffer has none, so svgf_invalidate_guide / a changed pointer or pitch are the signals)

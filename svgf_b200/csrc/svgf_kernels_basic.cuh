@@ -6,16 +6,22 @@
 
 namespace svgf {
 
-struct GBufView {  // pitch-linear G-buffer planes (include/svgf.h svgf_gbuffer), pitches in bytes
+struct GBufView {  // G-buffer planes (include/svgf.h svgf_gbuffer): pitch-linear memory (pitches in bytes) or texture objects
     const char *normal, *uv, *motion;
     size_t normal_pitch, uv_pitch, motion_pitch;
+    int tex;   // bit 0 normal, 1 uv, 2 motion: the "pointer" is a cudaTextureObject_t (SVGF_PITCH_TEXTURE) over a cudaArray in
+               // the reference's channel format, fetched like src/Filter.cuh:182-207: tex2D at integer texel coordinates of a
+               // point-sampled, un-normalised texture (src/CudaUtil.h:88-95)
     __device__ __forceinline__ float4 mot(int x, int y) const {
+        if (tex & 4) return tex2D<float4>((cudaTextureObject_t)motion, (float)x, (float)y);
         return __ldg(reinterpret_cast<const float4 *>(motion + (size_t)y * motion_pitch) + x);
     }
     __device__ __forceinline__ ushort4 nrm(int x, int y) const {
+        if (tex & 1) return tex2D<ushort4>((cudaTextureObject_t)normal, (float)x, (float)y);
         return __ldg(reinterpret_cast<const ushort4 *>(normal + (size_t)y * normal_pitch) + x);
     }
     __device__ __forceinline__ ushort4 uvw(int x, int y) const {
+        if (tex & 2) return tex2D<ushort4>((cudaTextureObject_t)uv, (float)x, (float)y);
         return __ldg(reinterpret_cast<const ushort4 *>(uv + (size_t)y * uv_pitch) + x);
     }
 };

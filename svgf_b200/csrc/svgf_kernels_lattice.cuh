@@ -92,18 +92,20 @@ __device__ __forceinline__ void grid_dependency_launch() { asm volatile("griddep
 struct LtCentre { float2 nlc, nzc, kL, kZ; };          // centre luminance and depth NEGATED (one FADD2 per difference)
 struct LtNormal { float2 nx, ny, nz; };
 
-// one tap row (pair `si`) applied to the outputs it serves.  UNIF: ckn[] = -log2(kernel weight) + u*P(u) of the tile's one
-// normal, per tap class; the weight is 2^-(base) with nothing else to add.
+// one tap row (pair `si`) applied to the outputs it serves.  UNIF: un = 1 - sat(n.n) and pn = P(un) of the tile's one normal
+// are two tile constants; the exponent is still formed by the same single fma(-u, p, -base) as the general form, so a
+// pixel gets the same bits whichever form its tile takes (and whichever way the image is cut into tiles or bands).
 template <int TERMS, bool UNIF>
 __device__ __forceinline__ void lt_tap(PkAcc &A, const LtCentre &C, const LtNormal &N, const float4 &c0, const float4 &c1, const float4 &lz,
-                                       const float4 &n0, const float2 &n1, float ck, float cinv, const PkCoef &k) {
+                                       const float4 &n0, const float2 &n1, float ck, float cinv, const PkCoef &k, float un, float pn) {
     const float2 ql = make_float2(lz.x, lz.y), qz = make_float2(lz.z, lz.w);
     float2 base = __ffma2_rn(f2abs(__fadd2_rn(ql, C.nlc)), C.kL, f2bc(ck));
     const float2 tz = __fmul2_rn(f2abs(__fadd2_rn(qz, C.nzc)), C.kZ);
     base = __ffma2_rn(tz, f2bc(cinv), base);
     float2 w;
     if (UNIF) {
-        w = make_float2(fast_exp2(-base.x), fast_exp2(-base.y));
+        const float2 e = __ffma2_rn(f2bc(-un), f2bc(pn), f2neg(base));
+        w = make_float2(fast_exp2(e.x), fast_exp2(e.y));
     } else {
         float2 d = __fmul2_rn(N.nx, make_float2(n0.x, n0.y));            // (x*x' + y*y') + z*z', reference dot order
         d = __ffma2_rn(N.ny, make_float2(n0.z, n0.w), d);
@@ -124,15 +126,10 @@ __device__ __forceinline__ void lt_tap(PkAcc &A, const LtCentre &C, const LtNorm
     A.v = __ffma2_rn(__fmul2_rn(w, w), make_float2(c1.z, c1.w), A.v);
 }
 
-__device__ __forceinline__ constexpr int tap_class(int ax, int ay) {   // by squared length 1 2 4 5 8
-    const int l2 = ax * ax + ay * ay;
-    return l2 == 1 ? 0 : l2 == 2 ? 1 : l2 == 4 ? 2 : l2 == 5 ? 3 : 4;
-}
-
 template <int STEP, int TERMS, bool UNIF>
 __device__ __forceinline__ void lt_all_taps(PkAcc (&A)[kPkRows], const LtCentre (&C)[kPkRows], const LtNormal (&N)[kPkRows],
                                             const float4 *sC0, const float4 *sC1, const float4 *sLZ, const float4 *sN0,
-                                            const float2 *sN1, int row0, int pcol, const PkCoef &k, const float (&ckn)[5]) {
+                                            const float2 *sN1, int row0, int pcol, const PkCoef &k, float un, float pn) {
     using G = LatGeom<STEP>;
     static_assert(STEP % 2 == 0, "odd tap offsets break the pixel pairs: level 0 stays with the packed kernel");
 #pragma unroll
@@ -149,8 +146,7 @@ __device__ __forceinline__ void lt_all_taps(PkAcc (&A)[kPkRows], const LtCentre 
                 const int dy = t - j;
                 if (dy < -2 || dy > 2 || (dx == 0 && dy == 0)) continue;
                 const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
-                const float ck = UNIF ? ckn[tap_class(ax, ay)] : tap_neg_log2_kernel(ax, ay);
-                lt_tap<TERMS, UNIF>(A[j], C[j], N[j], c0, c1, lz, n0, n1, ck, tap_inv_len(ax, ay), k);
+                lt_tap<TERMS, UNIF>(A[j], C[j], N[j], c0, c1, lz, n0, n1, tap_neg_log2_kernel(ax, ay), tap_inv_len(ax, ay), k, un, pn);
             }
         }
     }
@@ -159,24 +155,14 @@ __device__ __forceinline__ void lt_all_taps(PkAcc (&A)[kPkRows], const LtCentre 
 // 32-pixel row segments of the guide (svgf_device.cuh): w = 0 only background / outside, 1 one normal (xyz), 2 mixed
 constexpr float kSegWild = 0.0f, kSegUniform = 1.0f, kSegMixed = 2.0f;
 
-// Persistent CTAs (two per SM) walk the tile list through a device-side counter.  Per tile:
-//   [colour TMA in flight]  segment test + depth derivatives of the tile (global loads, issued one tile ahead of their
-//   use)  ->  (mixed tile: TMA of the normal planes)  ->  wait  ->  taps  ->  normalise into registers  ->  __syncthreads
-//   ->  colour TMA of the NEXT tile  ->  requantise + store this tile from registers.
-// So the shared-memory tile is refilled while the epilogue (a fifth of a tile's instructions) and the next tile's
-// prologue run; the other resident CTA covers what is left of the load latency.  There is no room for a second tile
-// buffer: 72 bytes per staged pixel pair x 2 CTAs is the whole shared memory at dilation 16.
-//
 // LAST: the level's result is the caller's plane in the storage format (`out`); otherwise it is the next lattice
-// level's input (`dst`).  tile_counter: zero on entry (the previous level's launch zeroed it); this launch zeroes
-// next_counter for its successor.
+// level's input (`dst`).
 template <bool F32, int STEP, int TERMS, bool LAST>
 __global__ void __launch_bounds__(kPkThreads, 2)
 atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_constant__ CUtensorMap mC1,
                       const __grid_constant__ CUtensorMap mLZ, const __grid_constant__ CUtensorMap mN0,
                       const __grid_constant__ CUtensorMap mN1, LatticeArgs a, const float *__restrict__ guide_dz,
-                      const float4 *__restrict__ seg, LatticeColour dst, typename ColourPlane<F32>::texel *__restrict__ out,
-                      unsigned int *__restrict__ tile_counter, unsigned int *__restrict__ next_counter) {
+                      const float4 *__restrict__ seg, LatticeColour dst, typename ColourPlane<F32>::texel *__restrict__ out) {
     using G = LatGeom<STEP>;
     using CT = typename ColourPlane<F32>::texel;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
@@ -189,210 +175,149 @@ atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_cons
     float4 *sN0 = reinterpret_cast<float4 *>(smem + G::off_n0);
     float2 *sN1 = reinterpret_cast<float2 *>(smem + G::off_n1);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + G::off_misc);          // [0] colour planes, [1] normal planes
-    int *sNext = reinterpret_cast<int *>(smem + G::off_misc + 32);             // [2]: tile index for the next iteration, double-buffered
     float4 *sRed = reinterpret_cast<float4 *>(smem + G::off_misc + 64);        // 3 warp records of the segment test
 
     const int tid = threadIdx.x;
-    const int tiles_x = (a.W + kTileW - 1) / kTileW;
-    const int tiles_y = ((a.H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP)) * STEP;    // (row block, phase) pairs
-    const int n_tiles = tiles_x * tiles_y;
-    const int pcx = tid & (kPkPairs - 1), tg = tid / kPkPairs;
-    const int pcol = pcx + STEP;
-    const int row0 = tg * kPkRows + 2;
+    const int x0 = blockIdx.x * kTileW;
+    const int yblock = blockIdx.y / STEP, phase = blockIdx.y % STEP;
+    const int y0 = yblock * (G::tile_rows * STEP) + phase;
 
-    // tile -> origin.  Linear order: x fastest, then the STEP row phases of a row block, then row blocks, so tiles in
-    // flight at the same time share halo rows in L2.
-    auto tile_origin = [&](int tile, int &x0, int &yblock, int &phase) {
-        const int ty = tile / tiles_x;
-        x0 = (tile - ty * tiles_x) * kTileW;
-        yblock = ty / STEP;
-        phase = ty - yblock * STEP;
-    };
-    auto issue_colour = [&](int tile) {      // one thread
-        int x0, yblock, phase;
-        tile_origin(tile, x0, yblock, phase);
-        const int cx = x0 - 2 * STEP + kLatPadX;                       // 8-byte elements == pixels for the 16-byte-per-pair planes
-        const int cy = yblock * G::tile_rows - 2 + kLatPadY / STEP;     // row block of the first staged row (kLatPadY % STEP == 0)
-        mbar_expect_tx(&bar[0], 3 * G::plane16);
-        tma_load_3d(sC0, &mC0, cx, phase, cy, &bar[0]);
-        tma_load_3d(sC1, &mC1, cx, phase, cy, &bar[0]);
-        tma_load_3d(sLZ, &mLZ, cx, phase, cy, &bar[0]);
-    };
-
+    const int cx = x0 - 2 * STEP + kLatPadX;                       // 8-byte elements == pixels for the 16-byte-per-pair planes
+    const int cy = yblock * G::tile_rows - 2 + kLatPadY / STEP;     // row block of the first staged row (kLatPadY % STEP == 0)
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        tma_prefetch_descriptor(&mC0); tma_prefetch_descriptor(&mC1); tma_prefetch_descriptor(&mLZ);
-        tma_prefetch_descriptor(&mN0); tma_prefetch_descriptor(&mN1);
+        grid_dependency_wait();   // the previous level's planes are complete from here on (only this thread reads them)
+        mbar_expect_tx(&bar[0], 3 * G::plane16);
+        tma_load_3d(sC0, &mC0, cx, phase, cy, &bar[0]);
+        tma_load_3d(sC1, &mC1, cx, phase, cy, &bar[0]);
+        tma_load_3d(sLZ, &mLZ, cx, phase, cy, &bar[0]);
     }
-    grid_dependency_wait();   // the previous level's planes (and its zeroing of tile_counter) are complete from here on
-    if (tid == 0 && blockIdx.x == 0 && next_counter) *next_counter = 0;
-    int tile = blockIdx.x;    // the first gridDim.x tiles are taken statically; the counter hands out the rest
-    if (tid == 0 && tile < n_tiles) issue_colour(tile);
+
+    // ---- uniform-normal test over the 6 x 16 segments that cover the staged tile (guide data: not written by the
+    //      previous level; it runs while the colour planes are already in flight) ----
+    float4 sg = make_float4(0.f, 0.f, 0.f, kSegWild);
+    if (tid < 96) {
+        const int r = tid / 6, sx = (x0 >> 5) - 1 + (tid - r * 6);
+        const int gy = y0 + (r - 2) * STEP;
+        if (sx >= 0 && sx < a.segs_x && gy >= 0 && gy < a.H) sg = __ldg(seg + (size_t)gy * a.segs_x + sx);
+        const unsigned has = __ballot_sync(0xffffffffu, sg.w == kSegUniform);
+        const int leader = has ? (__ffs(has) - 1) : 0;
+        const float rx = __shfl_sync(0xffffffffu, sg.x, leader), ry = __shfl_sync(0xffffffffu, sg.y, leader),
+                    rz = __shfl_sync(0xffffffffu, sg.z, leader);
+        const bool ok = sg.w == kSegWild || (sg.w == kSegUniform && sg.x == rx && sg.y == ry && sg.z == rz);
+        const bool all_ok = __all_sync(0xffffffffu, ok);
+        if ((tid & 31) == 0) sRed[tid >> 5] = make_float4(rx, ry, rz, !all_ok ? kSegMixed : (has ? kSegUniform : kSegWild));
+    }
+    // depth derivatives of this thread's outputs (guide data as well)
+    const int pcx = tid & (kPkPairs - 1), tg = tid / kPkPairs;
+    const int gx = x0 + 2 * pcx;
+    const int pcol = pcx + STEP;
+    const int row0 = tg * kPkRows + 2;
+    float2 dz[kPkRows];
+#pragma unroll
+    for (int j = 0; j < kPkRows; j++) {
+        const int gy = y0 + (tg * kPkRows + j) * STEP;
+        dz[j] = (gx < a.W && gy < a.H) ? __ldg(reinterpret_cast<const float2 *>(guide_dz + (size_t)gy * a.W + gx)) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();   // barrier init + the segment records
+
+    bool uniform_n = a.uniform_tiles != 0;
+    float3 nref = make_float3(0.f, 0.f, 0.f);
+    {
+        bool have = false;
+#pragma unroll
+        for (int w = 0; w < 3; w++) {
+            const float4 r = sRed[w];
+            if (r.w == kSegMixed) uniform_n = false;
+            else if (r.w == kSegUniform) {
+                if (!have) { nref = make_float3(r.x, r.y, r.z); have = true; }
+                else if (r.x != nref.x || r.y != nref.y || r.z != nref.z) uniform_n = false;
+            }
+        }
+    }
+
+    if (!uniform_n && tid == 0) {
+        mbar_expect_tx(&bar[1], G::plane16 + G::plane8);
+        tma_load_3d(sN0, &mN0, cx, phase, cy, &bar[1]);
+        tma_load_3d(sN1, &mN1, cx >> 1, phase, cy, &bar[1]);
+    }
+    grid_dependency_launch();
 
     PkCoef k;
     k.k1 = a.k1; k.k2 = a.k2; k.k3 = a.k3; k.k4 = a.k4; k.k5 = a.k5;
-    uint32_t par0 = 0, par1 = 0;
-    int slot = 0;
+    float un, pn;
+    pk_normal_term<TERMS>(nref.x, nref.y, nref.z, nref.x, nref.y, nref.z, k, un, pn);
 
-    // prologue of a tile: the global loads that do not depend on the previous level (segment map, depth derivatives)
-    float4 sg;
-    float2 dz[kPkRows];
-    auto tile_prologue_loads = [&](int t) {
-        int x0, yblock, phase;
-        tile_origin(t, x0, yblock, phase);
-        const int y0 = yblock * (G::tile_rows * STEP) + phase;
-        sg = make_float4(0.f, 0.f, 0.f, kSegWild);
-        if (tid < 96) {
-            const int r = tid / 6, sx = (x0 >> 5) - 1 + (tid - r * 6);
-            const int gy = y0 + (r - 2) * STEP;
-            if (sx >= 0 && sx < a.segs_x && gy >= 0 && gy < a.H) sg = __ldg(seg + (size_t)gy * a.segs_x + sx);
-        }
-        const int gx = x0 + 2 * pcx;
+    mbar_wait_or_trap(&bar[0], 0);
+
+    LtCentre C[kPkRows];
+    LtNormal N[kPkRows];
+    PkAcc A[kPkRows];
+    bool live0[kPkRows], live1[kPkRows];
+    bool any_live = false;
 #pragma unroll
-        for (int j = 0; j < kPkRows; j++) {
-            const int gy = y0 + (tg * kPkRows + j) * STEP;
-            dz[j] = (gx < a.W && gy < a.H) ? __ldg(reinterpret_cast<const float2 *>(guide_dz + (size_t)gy * a.W + gx)) : make_float2(0.f, 0.f);
-        }
-    };
-    if (tile < n_tiles) tile_prologue_loads(tile);
+    for (int j = 0; j < kPkRows; j++) {
+        const int si = (row0 + j) * G::pairs + pcol;
+        const float4 c0 = sC0[si], c1 = sC1[si], lz = sLZ[si];
+        const int gy = y0 + (tg * kPkRows + j) * STEP;
+        A[j].S = f2bc(1.0f);                                                       // :567-568
+        A[j].r = make_float2(c0.x, c0.y); A[j].g = make_float2(c0.z, c0.w);
+        A[j].b = make_float2(c1.x, c1.y); A[j].v = make_float2(c1.z, c1.w);
+        C[j].nlc = make_float2(-lz.x, -lz.y);
+        C[j].nzc = make_float2(-lz.z, -lz.w);
+        const bool inside = (gx < a.W) && (gy < a.H);
+        live0[j] = inside && (lz.z != kBackgroundZ);                               // :554: background passes through
+        live1[j] = inside && (lz.w != kBackgroundZ);
+        any_live |= live0[j] | live1[j];
+        C[j].kL = make_float2(a.kL_scale * rsqrtf(1e-10f + c1.z), a.kL_scale * rsqrtf(1e-10f + c1.w));   // :562
+        C[j].kZ = make_float2(__fdividef(a.kZ_scale, fmaxf(dz[j].x, 1e-6f)), __fdividef(a.kZ_scale, fmaxf(dz[j].y, 1e-6f)));   // :563
+        N[j].nx = N[j].ny = N[j].nz = make_float2(0.f, 0.f);
+    }
 
-    while (tile < n_tiles) {
-        int x0, yblock, phase;
-        tile_origin(tile, x0, yblock, phase);
-        const int y0 = yblock * (G::tile_rows * STEP) + phase;
-        const int gx = x0 + 2 * pcx;
-
-        // ---- uniform-normal test over the 6 x 16 segments that cover the staged tile ----
-        if (tid < 96) {
-            const unsigned has = __ballot_sync(0xffffffffu, sg.w == kSegUniform);
-            const int leader = has ? (__ffs(has) - 1) : 0;
-            const float rx = __shfl_sync(0xffffffffu, sg.x, leader), ry = __shfl_sync(0xffffffffu, sg.y, leader),
-                        rz = __shfl_sync(0xffffffffu, sg.z, leader);
-            const bool ok = sg.w == kSegWild || (sg.w == kSegUniform && sg.x == rx && sg.y == ry && sg.z == rz);
-            const bool all_ok = __all_sync(0xffffffffu, ok);
-            if ((tid & 31) == 0) sRed[tid >> 5] = make_float4(rx, ry, rz, !all_ok ? kSegMixed : (has ? kSegUniform : kSegWild));
-        }
-        if (tid == 0) sNext[slot] = (int)(atomicAdd(tile_counter, 1u) + gridDim.x);   // consumed after the taps
-        __syncthreads();   // the segment records (first tile: also the barrier init)
-
-        bool uniform_n = a.uniform_tiles != 0;
-        float3 nref = make_float3(0.f, 0.f, 0.f);
-        {
-            bool have = false;
-#pragma unroll
-            for (int w = 0; w < 3; w++) {
-                const float4 r = sRed[w];
-                if (r.w == kSegMixed) uniform_n = false;
-                else if (r.w == kSegUniform) {
-                    if (!have) { nref = make_float3(r.x, r.y, r.z); have = true; }
-                    else if (r.x != nref.x || r.y != nref.y || r.z != nref.z) uniform_n = false;
-                }
-            }
-        }
-        if (!uniform_n && tid == 0) {
-            const int cx = x0 - 2 * STEP + kLatPadX, cy = yblock * G::tile_rows - 2 + kLatPadY / STEP;
-            mbar_expect_tx(&bar[1], G::plane16 + G::plane8);
-            tma_load_3d(sN0, &mN0, cx, phase, cy, &bar[1]);
-            tma_load_3d(sN1, &mN1, cx >> 1, phase, cy, &bar[1]);
-        }
-
-        float ckn[5];
-        {
-            float un, pn;
-            pk_normal_term<TERMS>(nref.x, nref.y, nref.z, nref.x, nref.y, nref.z, k, un, pn);
-            const float cn = un * pn;
-            ckn[0] = tap_neg_log2_kernel(0, 1) + cn; ckn[1] = tap_neg_log2_kernel(1, 1) + cn; ckn[2] = tap_neg_log2_kernel(0, 2) + cn;
-            ckn[3] = tap_neg_log2_kernel(1, 2) + cn; ckn[4] = tap_neg_log2_kernel(2, 2) + cn;
-        }
-
-        mbar_wait_or_trap(&bar[0], par0);
-        par0 ^= 1;
-
-        LtCentre C[kPkRows];
-        LtNormal N[kPkRows];
-        PkAcc A[kPkRows];
-        bool live0[kPkRows], live1[kPkRows];
-        bool any_live = false;
+    if (uniform_n) {
+        if (__any_sync(0xffffffffu, any_live)) lt_all_taps<STEP, TERMS, true>(A, C, N, sC0, sC1, sLZ, sN0, sN1, row0, pcol, k, un, pn);
+    } else {
+        mbar_wait_or_trap(&bar[1], 0);
 #pragma unroll
         for (int j = 0; j < kPkRows; j++) {
             const int si = (row0 + j) * G::pairs + pcol;
-            const float4 c0 = sC0[si], c1 = sC1[si], lz = sLZ[si];
-            const int gy = y0 + (tg * kPkRows + j) * STEP;
-            A[j].S = f2bc(1.0f);                                                       // :567-568
-            A[j].r = make_float2(c0.x, c0.y); A[j].g = make_float2(c0.z, c0.w);
-            A[j].b = make_float2(c1.x, c1.y); A[j].v = make_float2(c1.z, c1.w);
-            C[j].nlc = make_float2(-lz.x, -lz.y);
-            C[j].nzc = make_float2(-lz.z, -lz.w);
-            const bool inside = (gx < a.W) && (gy < a.H);
-            live0[j] = inside && (lz.z != kBackgroundZ);                               // :554: background passes through
-            live1[j] = inside && (lz.w != kBackgroundZ);
-            any_live |= live0[j] | live1[j];
-            C[j].kL = make_float2(a.kL_scale * rsqrtf(1e-10f + c1.z), a.kL_scale * rsqrtf(1e-10f + c1.w));   // :562
-            C[j].kZ = make_float2(__fdividef(a.kZ_scale, fmaxf(dz[j].x, 1e-6f)), __fdividef(a.kZ_scale, fmaxf(dz[j].y, 1e-6f)));   // :563
-            N[j].nx = N[j].ny = N[j].nz = make_float2(0.f, 0.f);
+            const float4 n0 = sN0[si];
+            const float2 n1 = sN1[si];
+            N[j].nx = make_float2(n0.x, n0.y); N[j].ny = make_float2(n0.z, n0.w); N[j].nz = n1;
         }
-
-        if (uniform_n) {
-            if (__any_sync(0xffffffffu, any_live)) lt_all_taps<STEP, TERMS, true>(A, C, N, sC0, sC1, sLZ, sN0, sN1, row0, pcol, k, ckn);
-        } else {
-            mbar_wait_or_trap(&bar[1], par1);
-            par1 ^= 1;
-#pragma unroll
-            for (int j = 0; j < kPkRows; j++) {
-                const int si = (row0 + j) * G::pairs + pcol;
-                const float4 n0 = sN0[si];
-                const float2 n1 = sN1[si];
-                N[j].nx = make_float2(n0.x, n0.y); N[j].ny = make_float2(n0.z, n0.w); N[j].nz = n1;
-            }
-            if (__any_sync(0xffffffffu, any_live)) lt_all_taps<STEP, TERMS, false>(A, C, N, sC0, sC1, sLZ, sN0, sN1, row0, pcol, k, ckn);
-        }
-
-        // ---- normalise into registers (:615); pixels that pass through take their clamped centre from the tile (:556) ----
-        float4 o0[kPkRows], o1[kPkRows];
-        float2 zc[kPkRows];
-#pragma unroll
-        for (int j = 0; j < kPkRows; j++) {
-            const float i0 = __frcp_rn(A[j].S.x), i1 = __frcp_rn(A[j].S.y);
-            o0[j] = make_float4(A[j].r.x * i0, A[j].g.x * i0, A[j].b.x * i0, A[j].v.x * (i0 * i0));
-            o1[j] = make_float4(A[j].r.y * i1, A[j].g.y * i1, A[j].b.y * i1, A[j].v.y * (i1 * i1));
-            zc[j] = make_float2(-C[j].nzc.x, -C[j].nzc.y);
-            if (!(live0[j] && live1[j])) {
-                const int si = (row0 + j) * G::pairs + pcol;
-                const float4 c0 = sC0[si], c1 = sC1[si];
-                if (!live0[j]) o0[j] = make_float4(c0.x, c0.z, c1.x, c1.z);
-                if (!live1[j]) o1[j] = make_float4(c0.y, c0.w, c1.y, c1.w);
-            }
-        }
-        fence_proxy_async();   // this tile's generic-proxy reads of the planes precede the async-proxy refill
-        __syncthreads();       // every thread is done with the tile in shared memory
-        const int next = sNext[slot];
-        slot ^= 1;
-        if (tid == 0 && next < n_tiles) issue_colour(next);
-        if (next < n_tiles) tile_prologue_loads(next);   // consumed after the stores below
-
-        // ---- store both pixels of the pair (:618) ----
-#pragma unroll
-        for (int j = 0; j < kPkRows; j++) {
-            const int gy = y0 + (tg * kPkRows + j) * STEP;
-            if (gx >= a.W || gy >= a.H) continue;
-            if (LAST) {
-                const size_t gi = (size_t)gy * a.W + gx;
-                const CT e0 = ColourPlane<F32>::encode(o0[j]), e1 = ColourPlane<F32>::encode(o1[j]);
-                if (F32) {
-                    out[gi] = e0; out[gi + 1] = e1;
-                } else {
-                    const uint2 u0 = *reinterpret_cast<const uint2 *>(&e0), u1 = *reinterpret_cast<const uint2 *>(&e1);
-                    *reinterpret_cast<uint4 *>(out + gi) = make_uint4(u0.x, u0.y, u1.x, u1.y);
-                }
-            } else {
-                lattice_store_pair<F32>(dst, lattice_index(gx, gy, a.pitch_pairs), o0[j], o1[j], zc[j]);
-            }
-        }
-        tile = next;
+        if (__any_sync(0xffffffffu, any_live)) lt_all_taps<STEP, TERMS, false>(A, C, N, sC0, sC1, sLZ, sN0, sN1, row0, pcol, k, 0.f, 0.f);
     }
-    grid_dependency_launch();
+
+    // ---- normalise and store both pixels of the pair (:615-618) ----
+#pragma unroll
+    for (int j = 0; j < kPkRows; j++) {
+        const int gy = y0 + (tg * kPkRows + j) * STEP;
+        if (gx >= a.W || gy >= a.H) continue;
+        const int si = (row0 + j) * G::pairs + pcol;
+        const float i0 = __frcp_rn(A[j].S.x), i1 = __frcp_rn(A[j].S.y);
+        float4 o0 = make_float4(A[j].r.x * i0, A[j].g.x * i0, A[j].b.x * i0, A[j].v.x * (i0 * i0));
+        float4 o1 = make_float4(A[j].r.y * i1, A[j].g.y * i1, A[j].b.y * i1, A[j].v.y * (i1 * i1));
+        if (!(live0[j] && live1[j])) {
+            const float4 c0 = sC0[si], c1 = sC1[si];
+            if (!live0[j]) o0 = make_float4(c0.x, c0.z, c1.x, c1.z);                 // :556 (clamped centre)
+            if (!live1[j]) o1 = make_float4(c0.y, c0.w, c1.y, c1.w);
+        }
+        if (LAST) {
+            const size_t gi = (size_t)gy * a.W + gx;
+            const CT e0 = ColourPlane<F32>::encode(o0), e1 = ColourPlane<F32>::encode(o1);
+            if (F32) {
+                out[gi] = e0; out[gi + 1] = e1;
+            } else {
+                const uint2 u0 = *reinterpret_cast<const uint2 *>(&e0), u1 = *reinterpret_cast<const uint2 *>(&e1);
+                *reinterpret_cast<uint4 *>(out + gi) = make_uint4(u0.x, u0.y, u1.x, u1.y);
+            }
+        } else {
+            const float4 lz = sLZ[si];
+            lattice_store_pair<F32>(dst, lattice_index(gx, gy, a.pitch_pairs), o0, o1, make_float2(lz.z, lz.w));
+        }
+    }
 }
 
 }  // namespace svgf

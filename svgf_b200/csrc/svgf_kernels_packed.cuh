@@ -241,8 +241,7 @@ template <bool F32, int STEP, int TERMS, int R = kPkRows, bool PREF = false, boo
 __global__ void __launch_bounds__(kPkPairs * (PackedGeom<STEP>::tile_rows / R), 2)
 atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, const float *__restrict__ guide_dz,
                      const typename ColourPlane<F32>::texel *__restrict__ in, typename ColourPlane<F32>::texel *__restrict__ out,
-                     typename ColourPlane<F32>::texel *__restrict__ hist_colour, LatticeColour lc, LatticeNormals ln, int lat_pitch_pairs,
-                     unsigned int *__restrict__ lat_next_counter) {
+                     typename ColourPlane<F32>::texel *__restrict__ hist_colour, LatticeColour lc, LatticeNormals ln, int lat_pitch_pairs) {
     using G = PackedGeom<STEP>;
     constexpr int kThreads = kPkPairs * (G::tile_rows / R);   // R = 3: 256 threads, R = 4: 192
     static_assert(G::tile_rows % R == 0, "row groups must tile the 12 rows");
@@ -259,7 +258,6 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     const int x0 = blockIdx.x * kTileW;
     const int yblock = blockIdx.y / STEP, phase = blockIdx.y % STEP;
     const int y0 = yblock * (G::tile_rows * STEP) + phase;
-    if (STAGED && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && lat_next_counter) *lat_next_counter = 0;   // the lattice level's tile counter
 
     // ---- stage the tile, one pixel pair per thread and iteration; all global loads first ----
     // Uniform-normal tiles: when every in-image texel the tile stages (halo included) carries the same non-zero

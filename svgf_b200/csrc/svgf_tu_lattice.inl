@@ -22,10 +22,8 @@ svgf_status launch_lattice(svgf_ctx *c, const AtrousTiledArgs &t, int guide_slot
     a.uniform_tiles = t.uniform_tiles;
     const CUtensorMap *m = L.map[t.level];
     const int q = src * 3;
-    const int tiles = ((c->W + kTileW - 1) / kTileW) * (((c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP)) * STEP);
-    const int resident = 2 * c->num_sms;          // __launch_bounds__(256, 2): two CTAs per SM, every one of them persistent
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(tiles < resident ? tiles : resident);
+    cfg.gridDim = dim3((c->W + kTileW - 1) / kTileW, ((c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP)) * STEP);
     cfg.blockDim = dim3(kPkThreads);
     cfg.dynamicSmemBytes = G::smem_bytes;
     cfg.stream = s;
@@ -34,10 +32,8 @@ svgf_status launch_lattice(svgf_ctx *c, const AtrousTiledArgs &t, int guide_slot
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    // tile counters: one per level, each zeroed by the launch before it (the first level of a staged run zeroes level+1's)
-    unsigned int *counter = c->tile_counters + t.level, *next_counter = t.level < 7 ? c->tile_counters + t.level + 1 : nullptr;
     SVGF_CUDA(c, cudaLaunchKernelEx(&cfg, kern, m[q + 0], m[q + 1], m[q + 2], m[6], m[7], a, (const float *)c->guide[guide_slot].dz,
-                                    (const float4 *)c->guide[guide_slot].seg, L.sc[1 - src], (CT *)out, counter, next_counter));
+                                    (const float4 *)c->guide[guide_slot].seg, L.sc[1 - src], (CT *)out));
     c->launches++;
     return SVGF_OK;
 }

@@ -14,7 +14,7 @@ svgf_status launch_atrous_packed(svgf_ctx *c, AtrousTiledArgs a, int guide_slot,
     SVGF_CUDA(c, configure_smem_once(configured, c->device, kern, G::smem_bytes));
     const dim3 grid((c->W + kTileW - 1) / kTileW, ((c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP)) * STEP);
     kern<<<grid, kPkPairs * (G::tile_rows / R), G::smem_bytes, s>>>(a, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in, (CT *)out,
-                                                 (CT *)hist_colour, LatticeColour{nullptr, nullptr, nullptr}, LatticeNormals{nullptr, nullptr}, 0, nullptr);
+                                                 (CT *)hist_colour, LatticeColour{nullptr, nullptr, nullptr}, LatticeNormals{nullptr, nullptr}, 0);
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
     return SVGF_OK;

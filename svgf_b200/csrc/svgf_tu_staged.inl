@@ -14,7 +14,7 @@ svgf_status launch_staged(svgf_ctx *c, AtrousTiledArgs a, int guide_slot, const 
     SVGF_CUDA(c, configure_smem_once(configured, c->device, kern, G::smem_bytes));
     const dim3 grid((c->W + kTileW - 1) / kTileW, ((c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP)) * STEP);
     kern<<<grid, kPkThreads, G::smem_bytes, s>>>(a, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in, (CT *)nullptr,
-                                                 (CT *)hist_colour, c->lat.sc[dst], c->lat.sn, c->lat.pitch_pairs, c->tile_counters + a.level + 1);
+                                                 (CT *)hist_colour, c->lat.sc[dst], c->lat.sn, c->lat.pitch_pairs);
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
     return SVGF_OK;

@@ -84,4 +84,63 @@ int svgf_synth_frame_device(const svgf_synth_cfg *cfg, void *position, void *nor
     return (int)cudaGetLastError();
 }
 
+// ---- texture-backed G-buffers: what the reference's GL interop hands the filter (src/CudaUtil.h:68-99: one cudaArray per
+// attachment, a texture object with a zeroed cudaTextureDesc - element reads, point filter, un-normalised coordinates).
+// Here the arrays are plain cudaMallocArray allocations filled from linear device planes; no GL involved.
+struct svgf_synth_texgbuf {
+    int W, H;
+    cudaArray_t arr[3];               // normal, uv, motion
+    cudaTextureObject_t tex[3];
+};
+
+int svgf_synth_texgbuf_create(int W, int H, svgf_synth_texgbuf **out) {
+    if (!out || W <= 0 || H <= 0) return 1;
+    svgf_synth_texgbuf *t = new svgf_synth_texgbuf();
+    t->W = W; t->H = H;
+    for (int i = 0; i < 3; i++) { t->arr[i] = nullptr; t->tex[i] = 0; }
+    for (int i = 0; i < 3; i++) {
+        const cudaChannelFormatDesc d = (i == 2) ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<ushort4>();
+        cudaError_t e = cudaMallocArray(&t->arr[i], &d, W, H);
+        if (e == cudaSuccess) {
+            cudaResourceDesc rd;
+            memset(&rd, 0, sizeof(rd));
+            rd.resType = cudaResourceTypeArray;
+            rd.res.array.array = t->arr[i];
+            cudaTextureDesc td;
+            memset(&td, 0, sizeof(td));                  // src/CudaUtil.h:88-95
+            td.readMode = cudaReadModeElementType;
+            e = cudaCreateTextureObject(&t->tex[i], &rd, &td, nullptr);
+        }
+        if (e != cudaSuccess) {
+            for (int k = 0; k < 3; k++) { if (t->tex[k]) cudaDestroyTextureObject(t->tex[k]); if (t->arr[k]) cudaFreeArray(t->arr[k]); }
+            delete t;
+            return (int)e;
+        }
+    }
+    *out = t;
+    return 0;
+}
+
+void svgf_synth_texgbuf_destroy(svgf_synth_texgbuf *t) {
+    if (!t) return;
+    for (int k = 0; k < 3; k++) { if (t->tex[k]) cudaDestroyTextureObject(t->tex[k]); if (t->arr[k]) cudaFreeArray(t->arr[k]); }
+    delete t;
+}
+
+// Dense linear DEVICE planes -> the arrays (asynchronous on `stream`).
+int svgf_synth_texgbuf_upload(svgf_synth_texgbuf *t, const void *normal, const void *uv, const void *motion, void *stream) {
+    if (!t || !normal || !uv || !motion) return 1;
+    const size_t W = (size_t)t->W;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpy2DToArrayAsync(t->arr[0], 0, 0, normal, W * 8, W * 8, t->H, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpy2DToArrayAsync(t->arr[1], 0, 0, uv, W * 8, W * 8, t->H, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpy2DToArrayAsync(t->arr[2], 0, 0, motion, W * 16, W * 16, t->H, cudaMemcpyDeviceToDevice, s);
+    return (int)e;
+}
+
+// tex[0..2] = cudaTextureObject_t of normal, uv, motion
+void svgf_synth_texgbuf_objects(const svgf_synth_texgbuf *t, unsigned long long tex[3]) {
+    for (int k = 0; k < 3; k++) tex[k] = t ? (unsigned long long)t->tex[k] : 0ull;
+}
+
 }  // extern "C"

@@ -50,6 +50,52 @@ class GBuffer:
                 t.zero_()
 
 
+class TextureGBuffer:
+    """A ``framebuffer`` as the reference's filter receives it (src/App.cu:473-475): three cudaTextureObject_t over
+    cudaArrays (src/CudaUtil.h:68-99).  Filled from a linear ``GBuffer`` (the stand-in for the rasteriser's GL
+    attachments); ``as_struct`` hands the texture objects to the C ABI with SVGF_PITCH_TEXTURE."""
+
+    def __init__(self, width, height, device):
+        self.device = device
+        self._h = C.c_void_p()
+        with torch.cuda.device(device):
+            rc = _lib.synth_lib().svgf_synth_texgbuf_create(width, height, C.byref(self._h))
+        if rc:
+            raise RuntimeError(f"svgf_synth_texgbuf_create failed ({rc})")
+        tex = (C.c_ulonglong * 3)()
+        _lib.synth_lib().svgf_synth_texgbuf_objects(self._h, C.byref(tex))
+        self.normal_tex, self.uv_tex, self.motion_tex = int(tex[0]), int(tex[1]), int(tex[2])
+
+    def upload(self, gbuf):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = _lib.synth_lib().svgf_synth_texgbuf_upload(self._h, _ptr(gbuf.normal), _ptr(gbuf.uv), _ptr(gbuf.motion), C.c_void_p(stream))
+        if rc:
+            raise RuntimeError(f"svgf_synth_texgbuf_upload failed ({rc})")
+
+    def as_struct(self):
+        g = SvgfGBuffer()
+        g.position_id, g.position_pitch = None, 0
+        g.normal_mat, g.normal_pitch = self.normal_tex, _lib.SVGF_PITCH_TEXTURE
+        g.uv_inst, g.uv_pitch = self.uv_tex, _lib.SVGF_PITCH_TEXTURE
+        g.motion_depth, g.motion_pitch = self.motion_tex, _lib.SVGF_PITCH_TEXTURE
+        return g
+
+    def zero_(self):
+        pass
+
+    def close(self):
+        if self._h:
+            _lib.synth_lib().svgf_synth_texgbuf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class SvgfFilter:
     """The SVGF stage of the reference's frame loop, driven through libsvgf_b200.so.
 

@@ -86,7 +86,9 @@ def test_taa_kernel_against_the_oracle_over_a_short_sequence(size, storage):
         got = npy(f.TAA())
         # teacher-forced: the kernel's history is the oracle's, so that one resolve is compared, not an accumulated drift
         if storage == "f32":
-            assert np.abs(got.astype(np.float64) - want).max() <= 2e-5, f"frame {t}"
+            # north_star's bar: 1e-4.  The kernel takes pow(x, 1/2.4) as ex2(lg2(x) / 2.4) and sqrt as MUFU.SQRT (2^-21 each)
+            # and contracts the YUV dot products; outputs are in [0, 1]
+            assert np.abs(got.astype(np.float64) - want).max() <= 1e-4, f"frame {t}"
         else:
             assert_close(got, want, storage, f"TAA frame {t} {size}", max_flips=0.02)
         assert np.all(got[..., 3] == 1.0)

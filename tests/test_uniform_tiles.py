@@ -80,12 +80,14 @@ def test_planar_scene_every_level_against_the_oracle_and_against_the_general_for
 
 
 @pytest.mark.parametrize("storage", ["f16", "f32"])
-def test_benchmark_scene_sequence_is_bit_identical_with_and_without_the_shortcut(storage):
-    # level-by-level path (packed kernel): the shortcut forms the exponent with the same single FMA as the general form
+@pytest.mark.parametrize("base_flags", [0, _lib.SVGF_FLAG_NO_STAGED_LEVELS])
+def test_benchmark_scene_sequence_is_bit_identical_with_and_without_the_shortcut(storage, base_flags):
+    # both the staged run (lattice kernel: uniformity from the segment map) and the level-by-level path (packed kernel:
+    # uniformity from the staged texels) form the exponent with the same single FMA as the general form
     W, H, N = 1280, 720, 6
     a, b = SvgfFilter(W, H, storage=storage), SvgfFilter(W, H, storage=storage)
-    a.params.flags = _lib.SVGF_FLAG_NO_STAGED_LEVELS
-    b.params.flags = _lib.SVGF_FLAG_NO_STAGED_LEVELS | _lib.SVGF_FLAG_NO_UNIFORM_TILES
+    a.params.flags = base_flags
+    b.params.flags = base_flags | _lib.SVGF_FLAG_NO_UNIFORM_TILES
     a.Reset(); b.Reset()
     for t in range(N):
         planes = synth.frame_host(W, H, t, storage=storage)
