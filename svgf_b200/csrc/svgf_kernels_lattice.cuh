@@ -30,6 +30,10 @@
 #include "svgf_device.cuh"
 #include "svgf_kernels_packed.cuh"
 
+#ifndef SVGF_EXP
+#define SVGF_EXP 0      // build-time experiment selector (tools/build_exp.sh); 0 = the shipped form
+#endif
+
 namespace svgf {
 
 template <int STEP> struct LatGeom {
@@ -96,16 +100,15 @@ struct LtNormal { float2 nx, ny, nz; };
 // are two tile constants; the exponent is still formed by the same single fma(-u, p, -base) as the general form, so a
 // pixel gets the same bits whichever form its tile takes (and whichever way the image is cut into tiles or bands).
 template <int TERMS, bool UNIF>
-__device__ __forceinline__ void lt_tap(PkAcc &A, const LtCentre &C, const LtNormal &N, const float4 &c0, const float4 &c1, const float4 &lz,
-                                       const float4 &n0, const float2 &n1, float ck, float cinv, const PkCoef &k, float un, float pn) {
+__device__ __forceinline__ float2 lt_weight(const LtCentre &C, const LtNormal &N, const float4 &lz, const float4 &n0, const float2 &n1,
+                                            float ck, float cinv, const PkCoef &k, float un, float pn) {
     const float2 ql = make_float2(lz.x, lz.y), qz = make_float2(lz.z, lz.w);
     float2 base = __ffma2_rn(f2abs(__fadd2_rn(ql, C.nlc)), C.kL, f2bc(ck));
     const float2 tz = __fmul2_rn(f2abs(__fadd2_rn(qz, C.nzc)), C.kZ);
     base = __ffma2_rn(tz, f2bc(cinv), base);
-    float2 w;
+    float2 e;
     if (UNIF) {
-        const float2 e = __ffma2_rn(f2bc(-un), f2bc(pn), f2neg(base));
-        w = make_float2(fast_exp2(e.x), fast_exp2(e.y));
+        e = __ffma2_rn(f2bc(-un), f2bc(pn), f2neg(base));
     } else {
         float2 d = __fmul2_rn(N.nx, make_float2(n0.x, n0.y));            // (x*x' + y*y') + z*z', reference dot order
         d = __ffma2_rn(N.ny, make_float2(n0.z, n0.w), d);
@@ -116,9 +119,14 @@ __device__ __forceinline__ void lt_tap(PkAcc &A, const LtCentre &C, const LtNorm
         if (TERMS == 5) { p = __ffma2_rn(u, f2bc(k.k5), f2bc(k.k4)); p = __ffma2_rn(u, p, f2bc(k.k3)); p = __ffma2_rn(u, p, f2bc(k.k2)); }
         else p = __ffma2_rn(u, f2bc(k.k3), f2bc(k.k2));
         p = __ffma2_rn(u, p, f2bc(k.k1));
-        const float2 e = __ffma2_rn(f2neg(u), p, f2neg(base));
-        w = make_float2(fast_exp2(e.x), fast_exp2(e.y));
+        e = __ffma2_rn(f2neg(u), p, f2neg(base));
     }
+    return make_float2(fast_exp2(e.x), fast_exp2(e.y));
+}
+template <int TERMS, bool UNIF>
+__device__ __forceinline__ void lt_tap(PkAcc &A, const LtCentre &C, const LtNormal &N, const float4 &c0, const float4 &c1, const float4 &lz,
+                                       const float4 &n0, const float2 &n1, float ck, float cinv, const PkCoef &k, float un, float pn) {
+    const float2 w = lt_weight<TERMS, UNIF>(C, N, lz, n0, n1, ck, cinv, k, un, pn);
     A.S = __fadd2_rn(A.S, w);
     A.r = __ffma2_rn(w, make_float2(c0.x, c0.y), A.r);
     A.g = __ffma2_rn(w, make_float2(c0.z, c0.w), A.g);
