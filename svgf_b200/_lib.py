@@ -85,6 +85,21 @@ ABI = [
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 ]
 
+# include/svgf_band.h
+ABI += [
+    ("svgf_band_unique_id", C.c_int, [C.c_void_p]),
+    ("svgf_band_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                   C.POINTER(C.c_int32)]),
+    ("svgf_band_destroy", None, [C.c_void_p]),
+    ("svgf_band_rows", None, [C.c_void_p, C.POINTER(C.c_int32 * 4)]),
+    ("svgf_band_reset", C.c_int, [C.c_void_p, C.POINTER(SvgfFrameBuffers), C.c_void_p]),
+    ("svgf_band_frame", C.c_int, [C.c_void_p, C.POINTER(SvgfParams), C.POINTER(SvgfGBuffer * 2), C.POINTER(SvgfFrameBuffers),
+                                  C.c_void_p]),
+    ("svgf_band_sync", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("svgf_band_launch_count", C.c_uint64, [C.c_void_p]),
+    ("svgf_band_last_error", C.c_int, [C.c_void_p]),
+]
+
 SYNTH_ABI = [
     ("svgf_synth_frame_host", C.c_int, [C.POINTER(SynthCfg)] + [C.c_void_p] * 5 + [C.c_int]),
     ("svgf_synth_rows_host", C.c_int, [C.POINTER(SynthCfg), C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int]),

@@ -1,0 +1,317 @@
+// svgf_band.cu — include/svgf_band.h: one frame in horizontal bands, one band per GPU, halos exchanged with NCCL send/recv.
+//
+// What runs where, per frame (N = 5 levels; main = the caller's stream, side = the driver's exchange stream):
+//   main: [wait state exchange of frame t-1]  temporal + variance (whole local image)  level 0 (whole local image)
+//   side:                                                                              [after level 0] exchange STATE(t) ----.
+//   main: level 1 (band +- 8 rows)   level 2: boundary row blocks -> [ev]   level 2: interior row blocks                    |
+//   side:                                                              `-> exchange 16 rows of level 2's output -> [ev]     |
+//   main:                       [wait]  level 3: boundary row blocks -> [ev]   level 3: interior row blocks                 |
+//   side:                                                                `-> exchange 32 rows of level 3's output -> [ev]   |
+//   main:                                                      [wait]  level 4 (band rows) -> filter[0]                     |
+//   frame t+1, main: [wait] <------------------------------------------------------------------------------------------------'
+// Levels 0..2 do not exchange: their halos (2 + 4 + 8 rows), the variance pass's 7x7 window and the motion vectors' reach are
+// covered by computing those stages up to 17 + max_motion rows into the 32-row apron.  Only lattice planes travel for
+// the per-level exchanges (the level that follows reads them by TMA); whole padded rows, so one contiguous block per plane.
+//
+// NCCL is loaded at run time (dlopen "libnccl.so.2"): libsvgf_b200.so itself has no NCCL dependency, and inside a PyTorch
+// process the call lands in the library PyTorch has already loaded.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstring>
+#include <new>
+
+#include "../../include/svgf_band.h"
+#include "svgf_ctx.h"
+
+namespace {
+
+// ---- the slice of the NCCL API used here (nccl.h: stable since 2.7) ----------------------------------------------------
+struct NcclUniqueId { char internal[SVGF_BAND_UNIQUE_ID_BYTES]; };
+typedef struct ncclComm *NcclComm;
+constexpr int kNcclUint8 = 1;   // ncclDataType_t::ncclUint8
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*Send)(const void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    bool ok = false;
+};
+
+const NcclApi &nccl() {
+    static NcclApi api = [] {
+        NcclApi a;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            a.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (a.lib) break;
+        }
+        if (!a.lib) return a;
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(a.lib, "ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(a.lib, "ncclCommInitRank"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.lib, "ncclCommDestroy"));
+        a.Send = reinterpret_cast<decltype(a.Send)>(dlsym(a.lib, "ncclSend"));
+        a.Recv = reinterpret_cast<decltype(a.Recv)>(dlsym(a.lib, "ncclRecv"));
+        a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(a.lib, "ncclGroupStart"));
+        a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(a.lib, "ncclGroupEnd"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.GroupStart && a.GroupEnd;
+        return a;
+    }();
+    return api;
+}
+
+struct Plane {          // rows of a local image as one contiguous run per row range
+    char *base;         // address of local row 0
+    size_t row_bytes;
+};
+
+}  // namespace
+
+struct svgf_band {
+    svgf_ctx *ctx = nullptr;
+    int device = 0, rank = 0, world = 1, W = 0, H = 0;
+    int y0 = 0, y1 = 0, ly0 = 0, ly1 = 0;
+    NcclComm comm = nullptr;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_l0 = nullptr, ev_boundary[2] = {nullptr, nullptr}, ev_halo[2] = {nullptr, nullptr}, ev_state = nullptr;
+    bool state_pending = false;
+    int last_err = 0;
+
+    int band_lo() const { return y0 - ly0; }     // local row of the first owned row
+    int band_hi() const { return y1 - ly0; }     // local row one past the last owned row
+    int local_rows() const { return ly1 - ly0; }
+};
+
+namespace {
+
+svgf_status band_cuda(svgf_band *b, cudaError_t e) {
+    if (e == cudaSuccess) return SVGF_OK;
+    b->last_err = (int)e;
+    return SVGF_CUDA_ERROR;
+}
+svgf_status band_nccl(svgf_band *b, int r) {
+    if (r == 0) return SVGF_OK;
+    b->last_err = 10000 + r;    // ncclResult_t, offset so that it cannot be mistaken for a cudaError_t
+    return SVGF_CUDA_ERROR;
+}
+#define BAND_TRY(x)                       \
+    do {                                  \
+        const svgf_status st_ = (x);      \
+        if (st_ != SVGF_OK) return st_;   \
+    } while (0)
+
+// Refresh `rows` apron rows on each side of the band, for every plane, with the neighbours' band rows: ONE grouped
+// send/recv on the side stream.
+svgf_status exchange(svgf_band *b, const Plane *planes, int n_planes, int rows) {
+    const NcclApi &n = nccl();
+    const int lo = b->band_lo(), hi = b->band_hi();
+    BAND_TRY(band_nccl(b, n.GroupStart()));
+    for (int k = 0; k < n_planes; k++) {
+        const Plane &p = planes[k];
+        const size_t bytes = (size_t)rows * p.row_bytes;
+        if (b->rank > 0) {                    // my top band rows -> upper neighbour's bottom apron; its bottom band rows -> my top apron
+            BAND_TRY(band_nccl(b, n.Send(p.base + (size_t)lo * p.row_bytes, bytes, kNcclUint8, b->rank - 1, b->comm, b->side)));
+            BAND_TRY(band_nccl(b, n.Recv(p.base + (size_t)(lo - rows) * p.row_bytes, bytes, kNcclUint8, b->rank - 1, b->comm, b->side)));
+        }
+        if (b->rank + 1 < b->world) {
+            BAND_TRY(band_nccl(b, n.Send(p.base + (size_t)(hi - rows) * p.row_bytes, bytes, kNcclUint8, b->rank + 1, b->comm, b->side)));
+            BAND_TRY(band_nccl(b, n.Recv(p.base + (size_t)hi * p.row_bytes, bytes, kNcclUint8, b->rank + 1, b->comm, b->side)));
+        }
+    }
+    return band_nccl(b, n.GroupEnd());
+}
+
+}  // namespace
+
+extern "C" {
+
+svgf_status svgf_band_unique_id(void *id_out) {
+    if (!id_out) return SVGF_INVALID_ARG;
+    if (!nccl().ok) return SVGF_UNSUPPORTED;
+    NcclUniqueId id;
+    if (nccl().GetUniqueId(&id) != 0) return SVGF_CUDA_ERROR;
+    std::memcpy(id_out, &id, sizeof(id));
+    return SVGF_OK;
+}
+
+svgf_status svgf_band_create(svgf_band **out, int device, int rank, int world, int width, int full_height, svgf_storage storage,
+                             const void *unique_id, const int32_t *row_bounds) {
+    if (!out || world < 1 || rank < 0 || rank >= world || width <= 0 || full_height <= 0) return SVGF_INVALID_ARG;
+    if (world > 1 && !unique_id) return SVGF_INVALID_ARG;
+    *out = nullptr;
+    int y0, y1;
+    if (row_bounds) {
+        if (row_bounds[0] != 0 || row_bounds[world] != full_height) return SVGF_INVALID_ARG;
+        for (int g = 0; g < world; g++)
+            if (row_bounds[g + 1] <= row_bounds[g]) return SVGF_INVALID_ARG;
+        y0 = row_bounds[rank]; y1 = row_bounds[rank + 1];
+        if (world > 1)
+            for (int g = 0; g < world; g++)
+                if (row_bounds[g + 1] - row_bounds[g] < SVGF_BAND_APRON) return SVGF_UNSUPPORTED;   // a band must fill its neighbours' aprons
+    } else {
+        const int base = full_height / world, rem = full_height % world;
+        y0 = rank * base + (rank < rem ? rank : rem);
+        y1 = y0 + base + (rank < rem ? 1 : 0);
+        if (world > 1 && base < SVGF_BAND_APRON) return SVGF_UNSUPPORTED;
+    }
+    if (world > 1 && !nccl().ok) return SVGF_UNSUPPORTED;
+    svgf_band *b = new (std::nothrow) svgf_band();
+    if (!b) return SVGF_CUDA_ERROR;
+    b->device = device; b->rank = rank; b->world = world; b->W = width; b->H = full_height;
+    b->y0 = y0; b->y1 = y1;
+    b->ly0 = (world > 1 && y0 - SVGF_BAND_APRON > 0) ? y0 - SVGF_BAND_APRON : (world > 1 ? 0 : y0);
+    b->ly1 = (world > 1 && y1 + SVGF_BAND_APRON < full_height) ? y1 + SVGF_BAND_APRON : (world > 1 ? full_height : y1);
+    svgf_status st = svgf_create(&b->ctx, device, width, b->local_rows(), storage);
+    if (st != SVGF_OK) { delete b; return st; }
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking);
+    cudaEvent_t *evs[] = {&b->ev_l0, &b->ev_boundary[0], &b->ev_boundary[1], &b->ev_halo[0], &b->ev_halo[1], &b->ev_state};
+    for (cudaEvent_t *ev : evs)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    int nr = 0;
+    if (e == cudaSuccess && world > 1) {
+        NcclUniqueId id;
+        std::memcpy(&id, unique_id, sizeof(id));
+        nr = nccl().CommInitRank(&b->comm, world, id, rank);
+    }
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    if (e != cudaSuccess || nr != 0) { svgf_band_destroy(b); return SVGF_CUDA_ERROR; }
+    *out = b;
+    return SVGF_OK;
+}
+
+void svgf_band_destroy(svgf_band *b) {
+    if (!b) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(b->device);
+    if (b->side) cudaStreamSynchronize(b->side);
+    if (b->comm) nccl().CommDestroy(b->comm);
+    if (b->side) cudaStreamDestroy(b->side);
+    cudaEvent_t evs[] = {b->ev_l0, b->ev_boundary[0], b->ev_boundary[1], b->ev_halo[0], b->ev_halo[1], b->ev_state};
+    for (cudaEvent_t ev : evs)
+        if (ev) cudaEventDestroy(ev);
+    svgf_destroy(b->ctx);
+    if (prev >= 0 && prev != b->device) cudaSetDevice(prev);
+    delete b;
+}
+
+void svgf_band_rows(const svgf_band *b, int32_t rows[4]) {
+    if (!b || !rows) return;
+    rows[0] = b->y0; rows[1] = b->y1; rows[2] = b->ly0; rows[3] = b->ly1;
+}
+
+uint64_t svgf_band_launch_count(const svgf_band *b) { return b ? svgf_launch_count(b->ctx) : 0; }
+int svgf_band_last_error(const svgf_band *b) { return !b ? 0 : (b->last_err ? b->last_err : svgf_last_cuda_error(b->ctx)); }
+
+svgf_status svgf_band_sync(svgf_band *b, void *stream) {
+    if (!b) return SVGF_INVALID_ARG;
+    if (b->state_pending) {
+        BAND_TRY(band_cuda(b, cudaStreamWaitEvent((cudaStream_t)stream, b->ev_state, 0)));
+        b->state_pending = false;
+    }
+    return SVGF_OK;
+}
+
+svgf_status svgf_band_reset(svgf_band *b, const svgf_frame_buffers *bufs, void *stream) {
+    if (!b) return SVGF_INVALID_ARG;
+    BAND_TRY(svgf_band_sync(b, stream));
+    return svgf_reset(b->ctx, bufs, stream);
+}
+
+svgf_status svgf_band_frame(svgf_band *b, const svgf_params *params, const svgf_gbuffer gbuf[2], const svgf_frame_buffers *bufs,
+                            void *stream) {
+    if (!b || !params || !gbuf || !bufs) return SVGF_INVALID_ARG;
+    svgf_ctx *c = b->ctx;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int N = params->atrous_iterations;
+    if (b->world == 1) return svgf_frame(c, params, gbuf, bufs, stream);   // one band = the whole frame
+    if (N < 2 || N > 5) return SVGF_UNSUPPORTED;
+    if (bufs->ping_pong != 0 && bufs->ping_pong != 1) return SVGF_INVALID_ARG;
+    const int P = bufs->ping_pong;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    if (prev_dev != b->device) BAND_TRY(band_cuda(b, cudaSetDevice(b->device)));
+    struct Restore { int d, cur; ~Restore() { if (d >= 0 && d != cur) cudaSetDevice(d); } } restore{prev_dev, b->device};
+
+    // previous-frame state in the aprons: posted under the previous frame's levels
+    BAND_TRY(svgf_band_sync(b, stream));
+
+    // temporal + variance over the whole local image = svgf_frame with no a-trous level (variance output in filter[0])
+    svgf_params p0 = *params;
+    p0.atrous_iterations = 0;
+    BAND_TRY(svgf_frame(c, &p0, gbuf, bufs, stream));
+    if (!svgf::staged_run_possible(c, params, bufs->filter[0], bufs->filter[1], bufs->render[P], 0, N)) return SVGF_UNSUPPORTED;
+    BAND_TRY(svgf::lattice_prepare(c, s));
+    const int slot = c->guide_cur;
+    c->dispatch_n = 0;
+
+    // level 0 over the whole local image: it also writes the normal planes every later level reads in the apron, and the
+    // colour history of the apron rows is replaced by the neighbours' below
+    BAND_TRY(svgf::staged_level(c, params, slot, 0, 0, bufs->filter[0], 0, nullptr, bufs->render[P], 0, 0, false, s));
+    BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_l0, s)));
+    {   // next frame's previous-frame state: colour history (level 0's output), moments and history lengths are final now
+        BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, b->ev_l0, 0)));
+        const size_t ct = c->storage == SVGF_STORE_F32 ? 16 : 8, mt = c->storage == SVGF_STORE_F32 ? 8 : 4;
+        const Plane st[3] = {{(char *)bufs->render[P], (size_t)b->W * ct}, {(char *)bufs->moments[P], (size_t)b->W * mt},
+                             {(char *)bufs->history, (size_t)b->W}};
+        BAND_TRY(exchange(b, st, 3, SVGF_BAND_APRON));
+        BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_state, b->side)));
+        b->state_pending = true;
+    }
+
+    const int lo = b->band_lo(), hi = b->band_hi(), Hl = b->local_rows();
+    const int first_exchanged = 3;                 // levels >= 3 get their halo from the neighbours; 0..2 recompute theirs
+    int src = 0;                                   // lattice colour set holding the input of the next level
+    int n_halo = 0;
+    for (int l = 1; l < N; l++) {
+        const int S = 1 << l, B = 12 * S;          // rows per row block of this level's tile grid
+        const bool last = (l == N - 1);
+        // rows this level must produce: the band, plus what the not-exchanging levels above it still need around it
+        int reach = 0;
+        for (int j = l + 1; j < N && j < first_exchanged; j++) reach += 2 << j;
+        const int r0 = lo - reach > 0 ? lo - reach : 0, r1 = hi + reach < Hl ? hi + reach : Hl;
+        const int ybA = r0 / B, ybB = (r1 + B - 1) / B;
+        const bool feeds_exchange = !last && (l + 1 >= first_exchanged);
+        void *out = last ? bufs->filter[0] : nullptr;
+        const int kind = last ? 2 : 1;
+        if (l >= first_exchanged) BAND_TRY(band_cuda(b, cudaStreamWaitEvent(s, b->ev_halo[(l - first_exchanged) & 1], 0)));
+        if (!feeds_exchange) {
+            BAND_TRY(svgf::staged_level(c, params, slot, l, kind, nullptr, src, out, nullptr, ybA, ybB - ybA, false, s));
+        } else {
+            // boundary first: the row blocks holding the `halo` band rows next to each neighbour, then the exchange is
+            // posted, then the interior
+            const int halo = 2 << (l + 1);
+            int t1 = b->rank > 0 ? (lo + halo + B - 1) / B : ybA;                  // top boundary blocks [ybA, t1)
+            int b0 = b->rank + 1 < b->world ? (hi - halo) / B : ybB;               // bottom boundary blocks [b0, ybB)
+            if (t1 > ybB) t1 = ybB;
+            if (b0 < ybA) b0 = ybA;
+            if (t1 >= b0) {                        // short band: boundary blocks meet, nothing left to overlap with
+                BAND_TRY(svgf::staged_level(c, params, slot, l, kind, nullptr, src, out, nullptr, ybA, ybB - ybA, false, s));
+                t1 = b0 = ybB;
+            } else {
+                if (t1 > ybA) BAND_TRY(svgf::staged_level(c, params, slot, l, kind, nullptr, src, out, nullptr, ybA, t1 - ybA, false, s));
+                if (ybB > b0) BAND_TRY(svgf::staged_level(c, params, slot, l, kind, nullptr, src, out, nullptr, b0, ybB - b0, false, s));
+            }
+            cudaEvent_t evb = b->ev_boundary[n_halo & 1], evh = b->ev_halo[(l + 1 - first_exchanged) & 1];
+            BAND_TRY(band_cuda(b, cudaEventRecord(evb, s)));
+            BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, evb, 0)));
+            const svgf::LatticeColour &dst = c->lat.sc[1 - src];                   // this level's output planes
+            const size_t row_bytes = (size_t)c->lat.pitch_pairs * 16, pad = (size_t)svgf::kLatPadY * row_bytes;
+            const Plane pl[3] = {{(char *)dst.c0 + pad, row_bytes}, {(char *)dst.c1 + pad, row_bytes}, {(char *)dst.lz + pad, row_bytes}};
+            BAND_TRY(exchange(b, pl, 3, halo));
+            BAND_TRY(band_cuda(b, cudaEventRecord(evh, b->side)));
+            n_halo++;
+            if (b0 > t1) BAND_TRY(svgf::staged_level(c, params, slot, l, kind, nullptr, src, out, nullptr, t1, b0 - t1, false, s));
+        }
+        src = 1 - src;
+    }
+    return SVGF_OK;
+}
+
+}  // extern "C"

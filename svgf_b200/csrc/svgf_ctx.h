@@ -112,6 +112,11 @@ svgf_status atrous_packed_staged_f32(svgf_ctx *c, int terms, const AtrousTiledAr
 svgf_status atrous_lattice_f16(svgf_ctx *c, int terms, const AtrousTiledArgs &a, int guide_slot, int src, void *out, bool pdl, cudaStream_t s);
 svgf_status atrous_lattice_f32(svgf_ctx *c, int terms, const AtrousTiledArgs &a, int guide_slot, int src, void *out, bool pdl, cudaStream_t s);
 
+// svgf_api.cu, for the band driver (svgf_band.cu)
+svgf_status staged_level(svgf_ctx *c, const svgf_params *p, int guide_slot, int level, int kind, const void *in, int idx, void *out,
+                         void *hist_colour, int yb0, int nyb, bool pdl, cudaStream_t s);
+bool staged_run_possible(const svgf_ctx *c, const svgf_params *p, const void *a, const void *b, const void *hist_colour, int first, int n);
+
 // one a-trous level (a.level = 0..4) / levels 0+1 fused; terms = series terms of the normal weight (3, 4 or 5);
 // rows = outputs per thread and column of the packed kernel (3, or 4 with terms == 3)
 svgf_status atrous_packed_f16(svgf_ctx *c, int terms, int rows, const AtrousTiledArgs &a, int guide_slot, const void *in, void *out, void *hist_colour, cudaStream_t s);

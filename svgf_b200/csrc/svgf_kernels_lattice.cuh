@@ -55,6 +55,7 @@ struct LatticeArgs {
     float kL_scale, kZ_scale;   // log2e / phi_colour, log2e / (STEP * phi_depth)
     float k1, k2, k3, k4, k5;   // normal-term series coefficients
     int uniform_tiles;          // 0: never take the uniform-normal shortcut (SVGF_FLAG_NO_UNIFORM_TILES)
+    int yblock0;                // first row block of this launch (band driver: boundary rows first, svgf_band.cu)
 };
 
 // ---- TMA / mbarrier primitives (PTX ISA: cp.async.bulk.tensor, mbarrier) -----------------------------------------
@@ -187,7 +188,7 @@ atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_cons
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * kTileW;
-    const int yblock = blockIdx.y / STEP, phase = blockIdx.y % STEP;
+    const int yblock = blockIdx.y / STEP + a.yblock0, phase = blockIdx.y % STEP;
     const int y0 = yblock * (G::tile_rows * STEP) + phase;
 
     const int cx = x0 - 2 * STEP + kLatPadX;                       // 8-byte elements == pixels for the 16-byte-per-pair planes

@@ -256,7 +256,7 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * kTileW;
-    const int yblock = blockIdx.y / STEP, phase = blockIdx.y % STEP;
+    const int yblock = blockIdx.y / STEP + a.yblock0, phase = blockIdx.y % STEP;
     const int y0 = yblock * (G::tile_rows * STEP) + phase;
 
     // ---- stage the tile, one pixel pair per thread and iteration; all global loads first ----

@@ -20,10 +20,12 @@ svgf_status launch_lattice(svgf_ctx *c, const AtrousTiledArgs &t, int guide_slot
     a.kL_scale = t.kL_scale; a.kZ_scale = t.kZ_scale;
     a.k1 = t.k1; a.k2 = t.k2; a.k3 = t.k3; a.k4 = t.k4; a.k5 = t.k5;
     a.uniform_tiles = t.uniform_tiles;
+    a.yblock0 = t.yblock0;
     const CUtensorMap *m = L.map[t.level];
     const int q = src * 3;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((c->W + kTileW - 1) / kTileW, ((c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP)) * STEP);
+    const int all_yblocks = (c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP);
+    cfg.gridDim = dim3((c->W + kTileW - 1) / kTileW, (t.nyblocks > 0 ? t.nyblocks : all_yblocks) * STEP);
     cfg.blockDim = dim3(kPkThreads);
     cfg.dynamicSmemBytes = G::smem_bytes;
     cfg.stream = s;

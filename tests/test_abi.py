@@ -12,10 +12,13 @@ from svgf_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_functions():
-    src = open(os.path.join(ROOT, "include", "svgf.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(svgf_[a-z_0-9]+)\s*\(", src)))
+def header_functions(headers=("svgf.h", "svgf_band.h")):
+    names = set()
+    for h in headers:
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(svgf_[a-z_0-9]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_declares_the_north_star_entry_points():
