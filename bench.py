@@ -4,14 +4,19 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 4k|1080p|720p|8k] [--storage f16|f32]
   python bench.py --impl reference ...      # the reference's own kernels (oracle/_ref), else the CPU oracle
 
-A "step" is one frame of the synthetic camera-pan sequence through svgf_frame.  Default
-workload = BASELINE.json configs[2] (3840x2160 sequence, the configuration the <0.5 ms target is quoted on);
-with --gpus N every rank filters its own independent 4K stream (weak scaling, no data-path collective —
-BASELINE config 5's sharding).  Prints ONE JSON line (rank 0).
+A "step" is one frame of the synthetic camera-pan sequence through svgf_frame.  Default workload =
+BASELINE.json configs[2] (3840x2160 sequence, the configuration the <0.5 ms target is quoted on); with --gpus N every rank
+filters its own independent 4K stream (weak scaling, no data-path collective).  Prints ONE JSON line (rank 0) carrying,
+besides the contract's keys: `roofline`, `cpu_baseline`, `parity` (the oracle on a band of the same frames, teacher-forced),
+`general_case` (no uniform-normal tile shortcut), `e2e` with its PCIe ceiling, `stage_ms_per_frame` (incl. the TAA resolve),
+`streams_1080p` (BASELINE configs[4]: 64 independent 1080p streams over the N GPUs, concurrent CUDA streams per GPU) and,
+for N > 1, `bands` (BASELINE configs[3]: 8K frames in N bands through the native NCCL band driver, with a bit-identity check
+of the stitched bands against the whole frame filtered on one GPU).
 """
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import sys
 import threading
@@ -23,30 +28,44 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {"720p": (1280, 720), "1080p": (1920, 1080), "4k": (3840, 2160), "8k": (7680, 4320)}
 # algorithmic bytes per pixel per frame: each pass reads every plane it needs
 # once and writes each output once, reference layouts, steady state.
-BYTES_PER_PX = {"f16": {"temporal": 98, "variance": 17, "atrous_level": 40, "atrous_hist": 8},
-                "f32": {"temporal": 130, "variance": 33, "atrous_level": 56, "atrous_hist": 16}}
+BYTES_PER_PX = {"f16": {"temporal": 98, "variance": 17, "atrous_level": 40, "atrous_hist": 8, "taa": 24},
+                "f32": {"temporal": 130, "variance": 33, "atrous_level": 56, "atrous_hist": 16, "taa": 48}}
 IN_BYTES_PER_PX = {"f16": 8 + 8 + 16 + 8, "f32": 8 + 8 + 16 + 16}   # normal + uv + motion + noisy colour
 OUT_BYTES_PER_PX = {"f16": 8, "f32": 16}
+MIN_TIMED_MS = 100.0          # the K-step timed region is repeated until at least this much device time has been measured
+
+
+def workload_name(W, H, levels, world=1, kind="streams"):
+    base = f"BASELINE configs[2]: {W}x{H} camera-pan sequence, temporal + variance + {levels} a-trous levels"
+    return base + (f"; {world} independent streams, one per GPU" if world > 1 and kind == "streams" else "")
+
+
+def base_config(W, H, levels, storage):
+    """config keys shared by both arms (the driver compares them)."""
+    return {"workload": workload_name(W, H, levels), "width": W, "height": H, "atrous_levels": levels, "storage": storage,
+            "params": "reference defaults (history 24, depth 0.8, normal 0.9, phi colour 10, phi normal 128)", "seed": 0}
 
 
 def ncu_traffic_per_launch(args):
     """Mean dram__bytes_read + dram__bytes_write per a-trous launch from the committed `ncu --set full` capture of this
-    command (profiles/atrous_r01final.metrics.csv, five consecutive levels of one 4K fp16 frame), or None for any other
-    workload: the capture is evidence for the default configuration only."""
+    command (five consecutive levels of one 4K fp16 frame), or None for any other workload: the capture is evidence for the
+    default configuration only."""
     import csv
     if args.workload != "4k" or args.storage != "f16" or args.levels != 5 or args.flags or args.prefilter or args.reproj:
         return None, None
-    path = os.path.join(ROOT, "profiles", "atrous_r01final.metrics.csv")
-    if not os.path.exists(path):
-        path = os.path.join(ROOT, "profiles", "atrous_r01s8.metrics.csv")
-    try:
-        rows = {r[0]: r for r in csv.reader(open(path)) if r}
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        rd, wr = rows["dram__bytes_read.sum"], rows["dram__bytes_write.sum"]
-        per = [float(a) * scale[rd[1]] + float(b) * scale[wr[1]] for a, b in zip(rd[2:], wr[2:])]
-        return int(sum(per) / len(per)), "profiles/%s (ncu --set full, mean of %d levels)" % (os.path.basename(path), len(per))
-    except Exception:
-        return None, None
+    for name in ("atrous_r02.metrics.csv", "atrous_r01final.metrics.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        try:
+            rows = {r[0]: r for r in csv.reader(open(path)) if r}
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd, wr = rows["dram__bytes_read.sum"], rows["dram__bytes_write.sum"]
+            per = [float(a) * scale[rd[1]] + float(b) * scale[wr[1]] for a, b in zip(rd[2:], wr[2:])]
+            return int(sum(per) / len(per)), "profiles/%s (ncu --set full, mean of %d levels)" % (name, len(per))
+        except Exception:
+            pass
+    return None, None
 
 
 def measured_peaks():
@@ -136,14 +155,22 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
-def max_over_ranks(x, world):
+def _reduce(x, world, op):
     if world == 1:
         return x
     import torch
     import torch.distributed as dist
     t = torch.tensor([x], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
     return float(t.item())
+
+
+def max_over_ranks(x, world):
+    return _reduce(x, world, "MAX")
+
+
+def sum_over_ranks(x, world):
+    return _reduce(x, world, "SUM")
 
 
 def all_ranks(x, world):
@@ -158,16 +185,6 @@ def all_ranks(x, world):
     return [float(v) for v in t.tolist()]
 
 
-def sum_over_ranks(x, world):
-    if world == 1:
-        return x
-    import torch
-    import torch.distributed as dist
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
-
-
 class FrameRing:
     """R pre-generated frames of the pan sequence resident in HBM (procedural generator, CUDA)."""
 
@@ -179,87 +196,366 @@ class FrameRing:
         cdt = torch.float16 if storage == "f16" else torch.float32
         self.gbuf = [GBuffer(W, H, device) for _ in range(R)]
         self.colour = [torch.empty(H, W, 4, dtype=cdt, device=device) for _ in range(R)]
+        self.seed = seed
         for t in range(R):
             synth.frame_device(self.gbuf[t], self.colour[t], t, seed=seed)
         torch.cuda.synchronize()
 
+    def restore_colour(self, lo, hi):
+        """The filter consumes the noisy radiance in place; regenerate frames lo..hi-1 (outside any timed region)."""
+        from svgf_b200 import synth
+        for t in range(lo, hi):
+            synth.frame_device(self.gbuf[t % self.R], self.colour[t % self.R], t, seed=self.seed)
+
+
+class DeviceSequence:
+    """A SvgfFilter stepping through a FrameRing with zero copies: gbuf[P] / render[P] point straight at ring slot t."""
+
+    def __init__(self, W, H, dev, storage, ring, levels, flags=0, prefilter=0, reproj=0):
+        from svgf_b200 import SvgfFilter
+        from svgf_b200._lib import SvgfFrameBuffers, SvgfGBuffer
+        self.f = SvgfFilter(W, H, device=dev, storage=storage)
+        self.f.SpatialFilterSteps = levels
+        self.f.params.flags, self.f.params.variance_prefilter, self.f.params.reproj_mode = flags, prefilter, reproj
+        self.ring, self.R = ring, ring.R
+        self._G, self._B = SvgfGBuffer, SvgfFrameBuffers
+        self.calls = {}
+
+    def args(self, t):
+        if t not in self.calls:
+            f, ring, R = self.f, self.ring, self.R
+            P = t & 1
+            cur, prev = t % R, (t - 1) % R
+            g = (self._G * 2)()
+            g[P] = ring.gbuf[cur].as_struct()
+            g[1 - P] = ring.gbuf[prev].as_struct()
+            b = self._B()
+            b.render[P] = ring.colour[cur].data_ptr()
+            b.render[1 - P] = ring.colour[prev].data_ptr()
+            for k in range(2):
+                b.moments[k] = f.MomentsBuffer[k].data_ptr()
+                b.filter[k] = f.FilterBuffer[k].data_ptr()
+            b.history = f.HistoryLengthBuffer.data_ptr()
+            b.ping_pong = P
+            self.calls[t] = (g, b)
+        return self.calls[t]
+
+    def step(self, t, sptr):
+        g, b = self.args(t)
+        f = self.f
+        st = f.lib.svgf_frame(f._ctx, C.byref(f.params), C.byref(g), C.byref(b), sptr)
+        if st:
+            raise RuntimeError(f"svgf_frame -> {st} (cuda {f.lib.svgf_last_cuda_error(f._ctx)})")
+
+
+def pcie_ceiling(dev, h2d_bytes, d2h_bytes):
+    """Host<->device copy bandwidth of this GPU with both directions busy at once, from pinned memory - what bounds the e2e
+    figure.  Returns GB/s per direction and the time one step's transfers need at those rates."""
+    import torch
+    n = 256 << 20
+    hin, hout = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    din, dout = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    best = [0.0, 0.0]
+    for it in range(4):
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s1):
+            ev[0].record(s1)
+            for _ in range(3):
+                din.copy_(hin, non_blocking=True)
+            ev[1].record(s1)
+        with torch.cuda.stream(s2):
+            ev[2].record(s2)
+            for _ in range(3):
+                hout.copy_(dout, non_blocking=True)
+            ev[3].record(s2)
+        torch.cuda.synchronize()
+        if it:
+            best[0] = max(best[0], 3 * n / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9)
+            best[1] = max(best[1], 3 * n / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9)
+    step_ms = max(h2d_bytes / (best[0] * 1e9), d2h_bytes / (best[1] * 1e9)) * 1e3
+    return {"h2d_gbs": round(best[0], 2), "d2h_gbs": round(best[1], 2), "ms_per_step_at_ceiling": round(step_ms, 4),
+            "how": "3 x 256 MiB pinned copies per direction, both directions concurrently on two streams, best of 3"}
+
+
+def run_streams_1080p(args, rank, world, local):
+    """BASELINE configs[4]: 64 independent 1080p streams sharded over the N GPUs (stream s on GPU s mod N), every stream
+    with its own context, state and CUDA stream; frames of the resident streams of a GPU are issued round-robin."""
+    import torch
+    W, H = WORKLOADS["1080p"]
+    dev = torch.device("cuda", local)
+    total = 64
+    mine = [s for s in range(total) if s % world == rank]
+    R, Wm, K = 6, 6, max(4, args.stream_frames)
+    seqs, streams = [], []
+    for s in mine:
+        ring = FrameRing(W, H, R, args.storage, seed=s, device=dev)
+        seqs.append(DeviceSequence(W, H, dev, args.storage, ring, args.levels))
+        streams.append(torch.cuda.Stream(dev))
+    for q, cs in zip(seqs, streams):
+        with torch.cuda.stream(cs):
+            q.f.Reset()
+    torch.cuda.synchronize()
+    sp = [C.c_void_p(cs.cuda_stream) for cs in streams]
+
+    def run(t0, t1):
+        for t in range(t0, t1):
+            for q, cs, p in zip(seqs, streams, sp):
+                q.step(t, p)
+
+    run(0, Wm)
+    torch.cuda.synchronize()
+    for q in seqs:      # frames Wm.. reuse ring slots 0..: regenerate the colour planes the warm-up consumed
+        q.ring.restore_colour(Wm, Wm + K)
+    barrier(world)
+    main = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    for cs in streams:
+        cs.wait_event(e0)
+    launches0 = sum(q.f.launches for q in seqs)
+    # the ring holds R frames: time the steps in laps of R - 1 frames with the colour planes restored in between
+    ms = 0.0
+    t = Wm
+    done = 0
+    while done < K:
+        lap = min(R - 1, K - done)
+        e0.record(main)
+        for cs in streams:
+            cs.wait_event(e0)
+        run(t, t + lap)
+        for cs in streams:
+            main.wait_stream(cs)
+        e1.record(main)
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+        t += lap
+        done += lap
+        if done < K:
+            for q in seqs:
+                q.ring.restore_colour(t, t + min(R - 1, K - done))
+            torch.cuda.synchronize()
+    launches = sum(q.f.launches for q in seqs) - launches0
+    barrier(world)
+    ms_max = max_over_ranks(ms, world)
+    launches = sum_over_ranks(launches, world)
+    value = total * W * H * K / (ms_max * 1e-3) / 1e9
+    for q in seqs:
+        q.f.close()
+    return {"workload": f"BASELINE configs[4]: 64 independent {W}x{H} streams over {world} GPU(s), {len(mine)} resident per GPU on concurrent CUDA streams",
+            "value": round(value, 4), "unit": "Gpix/s", "frames_per_stream": K, "ms_per_frame_per_stream_slot": round(ms_max / K / max(1, len(mine)), 5),
+            "ms_total": round(ms_max, 3), "streams_per_gpu": len(mine), "gpu_launches": int(launches), "scaling": "strong (64 streams in total)"}
+
+
+def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames):
+    """K timed 8K frames in `world` bands through the native band driver + a bit-identity check on rank 0."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from svgf_b200 import SvgfFilter, synth
+    from svgf_b200.band_driver import BandDriver
+    from svgf_b200.bands import balanced_bounds
+    from svgf_b200.filter import GBuffer
+    dev = torch.device("cuda", local)
+    cdt = torch.float16 if args.storage == "f16" else torch.float32
+    full_g, full_c = GBuffer(W, H, dev), torch.empty(H, W, 4, dtype=cdt, device=dev)
+    bounds = None
+    if args.band_balance and world > 1:
+        # equal estimated work per band: background pixels (linear depth 0) are passed through by the a-trous levels
+        synth.frame_device(full_g, full_c, 0, seed=0)
+        live = (full_g.motion[..., 2] != 0).float().mean(dim=1).cpu().numpy()
+        bounds = balanced_bounds(live + args.band_bg_cost * (1.0 - live), world, min_rows=32)
+    bd = BandDriver(W, H, rank, world, dev, storage=args.storage, levels=args.levels, bounds=bounds)
+    sl = bd.local_rows()
+    R = Wm + K
+    ring_g = [GBuffer(W, bd.Height, dev) for _ in range(R)]
+    ring_c = [torch.empty(bd.Height, W, 4, dtype=cdt, device=dev) for _ in range(R)]
+    # ---- bit identity of the stitched bands against the whole frame on one GPU (rank 0), first frames after a reset ----
+    whole = None
+    if rank == 0 and check_frames:
+        whole = SvgfFilter(W, H, device=dev, storage=args.storage)
+        whole.SpatialFilterSteps = args.levels
+        whole.Reset()
+    bad = 0
+    bd.Reset()
+    ranges = [None] * world
+    if world > 1:
+        dist.all_gather_object(ranges, (bd.y0, bd.y1))
+    else:
+        ranges = [(bd.y0, bd.y1)]
+    for t in range(R):
+        synth.frame_device(full_g, full_c, t, seed=0)
+        ring_g[t].normal.copy_(full_g.normal[sl]); ring_g[t].uv.copy_(full_g.uv[sl]); ring_g[t].motion.copy_(full_g.motion[sl])
+        ring_c[t].copy_(full_c[sl])
+        if t < check_frames:
+            P = bd.PingPongInx
+            bd.Framebuffer[P] = ring_g[t]
+            bd.RenderBuffer[P].copy_(ring_c[t])
+            bd.Filter()
+            bd.sync()
+            mine = bd.result_band().contiguous()
+            if whole is not None:
+                whole.Framebuffer[P].normal.copy_(full_g.normal); whole.Framebuffer[P].uv.copy_(full_g.uv); whole.Framebuffer[P].motion.copy_(full_g.motion)
+                whole.RenderBuffer[P].copy_(full_c)
+                whole.Filter()
+                ref = whole.FilterBuffer[0]
+                bad += int((mine.view(torch.uint8) != ref[bd.y0:bd.y1].contiguous().view(torch.uint8)).sum())
+                for r in range(1, world):
+                    y0, y1 = ranges[r]
+                    buf = torch.empty((y1 - y0, W, 4), dtype=cdt, device=dev)
+                    dist.recv(buf, src=r)
+                    bad += int((buf.view(torch.uint8) != ref[y0:y1].contiguous().view(torch.uint8)).sum())
+                whole.EndFrame()
+            elif world > 1:
+                dist.send(mine, dst=0)
+            bd.EndFrame()
+    if whole is not None:
+        whole.close()
+        del whole
+    del full_g, full_c
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    # ---- timing: a fresh sequence, inputs consumed in place from the resident ring ----
+    stream = torch.cuda.current_stream(dev)
+    bd.Reset()
+    keep = bd.RenderBuffer
+
+    def step(t):
+        P = bd.PingPongInx
+        bd.Framebuffer[P] = ring_g[t]
+        bd.RenderBuffer[P] = ring_c[t]
+        bd.Filter()
+        bd.EndFrame()
+
+    for t in range(Wm):
+        step(t)
+    barrier(world)
+    launches0 = bd.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(Wm, Wm + K):
+        step(t)
+    bd.sync()                       # the state exchange posted under the last frame's levels completes inside the timed region
+    e1.record(stream)
+    barrier(world)
+    ms = e0.elapsed_time(e1)
+    ms_max = max_over_ranks(ms, world)
+    ms_by_rank = all_ranks(ms / K, world)
+    launches = sum_over_ranks(bd.launches - launches0, world)
+    rows = [int(v) for v in all_ranks(float(bd.Height), world)]
+    bad_total = int(sum_over_ranks(float(bad), world))
+    bd.RenderBuffer = keep
+    bd.close()
+    value = W * H * K / (ms_max * 1e-3) / 1e9
+    bpp = BYTES_PER_PX[args.storage]
+    frame_bytes = (bpp["temporal"] + bpp["variance"] + bpp["atrous_level"] * args.levels + (bpp["atrous_hist"] if args.levels else 0)) * W * H
+    peak, _ = measured_peaks()
+    return {"workload": f"BASELINE configs[3]: {W}x{H} frames in {world} horizontal band(s), native band driver (include/svgf_band.h): "
+                        "NCCL send/recv of 16 + 32 halo rows before levels 3 and 4, boundary row blocks first, state exchange under levels 1-4",
+            "value": round(value, 4), "unit": "Gpix/s", "ms_per_step": round(ms_max / K, 5), "steps": K, "warmup": Wm, "scaling": "strong",
+            "band_bounds": bounds, "local_rows_by_rank": rows, "ms_per_step_by_rank": [round(v, 4) for v in ms_by_rank],
+            "gpu_launches": int(launches),
+            "bit_identical_to_one_gpu": (bad_total == 0) if check_frames else None, "checked_frames": check_frames, "mismatching_bytes": bad_total,
+            "frac_of_n_gpu_hbm_peak": round(frame_bytes / (ms_max / K * 1e-3) / 1e9 / (peak * world), 4)}
+
 
 def run_ours(args, rank, world, local):
     import torch
-    from svgf_b200 import SvgfFilter, _lib
-    from svgf_b200._lib import SvgfFrameBuffers, SvgfGBuffer
     W, H = WORKLOADS[args.workload]
     dev = torch.device("cuda", local)
     K, Wm = args.steps, args.warmup
     R = min(K + Wm, args.ring)
     ring = FrameRing(W, H, R, args.storage, seed=rank, device=dev)
-    f = SvgfFilter(W, H, device=dev, storage=args.storage)
-    f.SpatialFilterSteps = args.levels
-    f.params.flags = args.flags
-    f.params.variance_prefilter = args.prefilter
-    f.params.reproj_mode = args.reproj
-    lib = f.lib
+    seq = DeviceSequence(W, H, dev, args.storage, ring, args.levels, args.flags, args.prefilter, args.reproj)
+    f = seq.f
     stream = torch.cuda.current_stream(dev)
     sptr = C.c_void_p(stream.cuda_stream)
-
-    # per-frame argument structs: gbuf[P] / render[P] point straight at ring slot t, [Q] at slot t-1 (no copies)
-    def frame_args(t):
-        P = t & 1
-        cur, prev = t % R, (t - 1) % R
-        g = (SvgfGBuffer * 2)()
-        g[P] = ring.gbuf[cur].as_struct()
-        g[1 - P] = ring.gbuf[prev].as_struct()
-        b = SvgfFrameBuffers()
-        b.render[P] = ring.colour[cur].data_ptr()
-        b.render[1 - P] = ring.colour[prev].data_ptr()
-        for k in range(2):
-            b.moments[k] = f.MomentsBuffer[k].data_ptr()
-            b.filter[k] = f.FilterBuffer[k].data_ptr()
-        b.history = f.HistoryLengthBuffer.data_ptr()
-        b.ping_pong = P
-        return g, b
-
-    calls = [frame_args(t) for t in range(Wm + K)]
+    lap = min(K, R - Wm) if R > Wm else 0
+    if lap < K:
+        raise RuntimeError(f"--ring {args.ring} holds fewer than warmup + steps = {Wm + K} frames of {W}x{H}")
     f.Reset()
-
-    def step(t):
-        g, b = calls[t]
-        st = lib.svgf_frame(f._ctx, C.byref(f.params), C.byref(g), C.byref(b), sptr)
-        if st:
-            raise RuntimeError(f"svgf_frame -> {st} (cuda {lib.svgf_last_cuda_error(f._ctx)})")
-
     for t in range(Wm):
-        step(t)
+        seq.step(t, sptr)
     barrier(world)
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.start()
     launches0 = f.launches
-    f.profile_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for t in range(Wm, Wm + K):
-        step(t)
-    e1.record(stream)
-    barrier(world)
-    sampler.stop_flag = True
-    ms = e0.elapsed_time(e1)
-    prof = f.profile_end()
+    # EXACTLY K steps per timed region; the region is repeated (same K frames, colour planes regenerated and the sequence
+    # re-warmed in between, untimed) until MIN_TIMED_MS of device time has been measured
+    total_ms, repeats, prof_acc, frames_acc = 0.0, 0, {"temporal_ms": 0.0, "variance_ms": 0.0, "atrous_ms": 0.0}, 0
+    while True:
+        f.profile_begin()
+        e0.record(stream)
+        for t in range(Wm, Wm + K):
+            seq.step(t, sptr)
+        e1.record(stream)
+        barrier(world)
+        total_ms += e0.elapsed_time(e1)
+        prof = f.profile_end()
+        for k in prof_acc:
+            prof_acc[k] += prof[k]
+        frames_acc += prof["frames"]
+        repeats += 1
+        if max_over_ranks(total_ms, world) >= MIN_TIMED_MS or repeats >= args.max_repeats:
+            break
+        ring.restore_colour(0, Wm + K)
+        f.Reset()
+        for t in range(Wm):
+            seq.step(t, sptr)
+        barrier(world)
     launches = f.launches - launches0
+    sampler.stop_flag = True
     sampler.join()
-    ms_max = max_over_ranks(ms, world)
-    value = world * W * H * K / (ms_max * 1e-3) / 1e9
+    ms_max = max_over_ranks(total_ms, world)
+    n_timed = K * repeats
+    value = world * W * H * n_timed / (ms_max * 1e-3) / 1e9
+    ms_per_step = ms_max / n_timed
+    stage = {k: round(v / max(1, frames_acc), 5) for k, v in prof_acc.items()}
+
+    # ---- TAA + sRGB resolve (the step after the path, reference src/App.cu:516-522) on the filtered frames, timed alone ----
+    f.TAA()
+    torch.cuda.synchronize()
+    n_taa = 32
+    e0.record(stream)
+    for _ in range(n_taa):
+        f.TAA()
+        f.EndFrame()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    taa_ms = e0.elapsed_time(e1) / n_taa
+    stage["taa_ms"] = round(taa_ms, 5)
+
+    # ---- general case: the same K frames with the uniform-normal tile shortcut off (a curved / normal-mapped scene) ----
+    general = None
+    if not (args.flags & 8) and not args.skip_extras:
+        ring.restore_colour(0, Wm + K)
+        gseq = DeviceSequence(W, H, dev, args.storage, ring, args.levels, args.flags | 8, args.prefilter, args.reproj)
+        gseq.f.Reset()
+        for t in range(Wm):
+            gseq.step(t, sptr)
+        barrier(world)
+        e0.record(stream)
+        for t in range(Wm, Wm + K):
+            gseq.step(t, sptr)
+        e1.record(stream)
+        barrier(world)
+        gms = max_over_ranks(e0.elapsed_time(e1), world) / K
+        general = {"ms_per_step": round(gms, 5), "value": round(world * W * H / (gms * 1e-3) / 1e9, 4), "unit": "Gpix/s",
+                   "what": "SVGF_FLAG_NO_UNIFORM_TILES: every tap evaluates the normal weight (no planar-tile shortcut)"}
+        gseq.f.close()
 
     # ---- end to end through the host-buffer entry point: pinned host inputs, H2D + frame + D2H per step ----
     from svgf_b200 import synth
-    import numpy as np
     n_host = 4
     cdt = torch.float16 if args.storage == "f16" else torch.float32
     host = []
+    ring.restore_colour(0, n_host)
     for t in range(n_host):
         hp = {"normal": torch.empty(H, W, 4, dtype=torch.int16).pin_memory(), "uv": torch.empty(H, W, 4, dtype=torch.int16).pin_memory(),
               "motion": torch.empty(H, W, 4, dtype=torch.float32).pin_memory(), "colour": torch.empty(H, W, 4, dtype=cdt).pin_memory()}
         src = ring.gbuf[t % R]
-        synth.frame_device(src, ring.colour[t % R], t, seed=rank)       # regenerate (the timed run consumed the colour)
         hp["normal"].copy_(src.normal); hp["uv"].copy_(src.uv); hp["motion"].copy_(src.motion); hp["colour"].copy_(ring.colour[t % R])
         host.append(hp)
     result = torch.empty(H, W, 4, dtype=cdt).pin_memory()
@@ -281,6 +577,24 @@ def run_ours(args, rank, world, local):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), world)
     e2e_value = world * W * H * Ke / (e2e_ms * 1e-3) / 1e9
     checksum = float(result.float().sum())       # the host-side read of the step's result
+    h2d, d2h = IN_BYTES_PER_PX[args.storage] * W * H, OUT_BYTES_PER_PX[args.storage] * W * H
+    ceiling = None
+    if not args.skip_extras:
+        barrier(world)          # all ranks measure their link at the same time: that is the condition the e2e number ran under
+        ceiling = pcie_ceiling(dev, h2d, d2h)
+        ceiling["ms_per_step_at_ceiling"] = round(max_over_ranks(ceiling["ms_per_step_at_ceiling"], world), 4)
+    del host, result
+    f.close()
+    del ring, seq
+    torch.cuda.empty_cache()
+
+    streams_rec = bands_rec = None
+    if not args.skip_extras:
+        streams_rec = run_streams_1080p(args, rank, world, local)
+        torch.cuda.empty_cache()
+        if world > 1:
+            bw, bh = WORKLOADS["8k"]
+            bands_rec = run_band_frames(args, rank, world, local, bw, bh, K=args.band_frames, Wm=4, check_frames=3)
 
     if rank != 0:
         return None
@@ -289,207 +603,165 @@ def run_ours(args, rank, world, local):
     bpp = BYTES_PER_PX[args.storage]
     n_levels = args.levels
     at_bytes = (bpp["atrous_level"] * n_levels + (bpp["atrous_hist"] if n_levels else 0)) * W * H
-    at_launches = max(1, (launches - 2 * K) // K) if n_levels else 0
-    at_ms_per_frame = prof["atrous_ms"] / max(1, prof["frames"])
+    at_launches = n_levels
+    at_ms = stage["atrous_ms"]
     frame_bytes = (bpp["temporal"] + bpp["variance"]) * W * H + at_bytes
-    achieved = at_bytes / (at_ms_per_frame * 1e-3) / 1e9 if n_levels and at_ms_per_frame > 0 else None
+    achieved = at_bytes / (at_ms * 1e-3) / 1e9 if n_levels and at_ms > 0 else None
+    cfg = base_config(W, H, n_levels, args.storage)
+    cfg["workload"] = workload_name(W, H, n_levels, world)
+    cfg.update({"frames_resident": R, "l2": "every step reads a fresh frame (%.0f MB of inputs > 126 MB L2)" % (IN_BYTES_PER_PX[args.storage] * W * H / 1e6),
+                "flags": args.flags, "variance_prefilter": args.prefilter, "reproj_mode": args.reproj,
+                "timed_region": f"{K} steps x {repeats} repeat(s) = {n_timed} frames, {ms_max:.1f} ms of device time"})
     line = {
         "metric": "svgf_frame_throughput", "value": round(value, 4), "unit": "Gpix/s", "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": round(ms_max / K, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms_per_step, 5), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 compute, %s storage" % ("fp16" if args.storage == "f16" else "fp32"), "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[2]: {W}x{H} camera-pan sequence, temporal + variance + {n_levels} a-trous levels"
-                               + (f"; {world} independent streams, one per GPU" if world > 1 else ""),
-                   "width": W, "height": H, "atrous_levels": n_levels, "storage": args.storage, "frames_resident": R,
-                   "l2": "every step reads a fresh frame (%.0f MB of inputs > 126 MB L2)" % (IN_BYTES_PER_PX[args.storage] * W * H / 1e6),
-                   "params": "reference defaults (history 24, depth 0.8, normal 0.9, phi colour 10, phi normal 128)", "flags": args.flags,
-                   "variance_prefilter": args.prefilter, "reproj_mode": args.reproj},
-        "e2e": {"value": round(e2e_value, 4), "unit": "Gpix/s", "h2d_bytes_per_step": IN_BYTES_PER_PX[args.storage] * W * H,
-                "d2h_bytes_per_step": OUT_BYTES_PER_PX[args.storage] * W * H, "ms_per_step": round(e2e_ms / Ke, 4), "steps": Ke,
-                "api": "svgf_frame_host (pinned host buffers; copy-in, kernels and copy-out of consecutive frames overlap on three streams; timed region starts with the pipeline drained)", "result_checksum": checksum},
+        "config": cfg,
+        "e2e": {"value": round(e2e_value, 4), "unit": "Gpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": round(e2e_ms / Ke, 4), "steps": Ke,
+                "api": "svgf_frame_host (pinned host buffers; copy-in, kernels and copy-out of consecutive frames overlap on three streams; timed region starts with the pipeline drained)",
+                "result_checksum": checksum, "pcie_ceiling": ceiling,
+                "frac_of_pcie_ceiling": round(ceiling["ms_per_step_at_ceiling"] / (e2e_ms / Ke), 4) if ceiling else None},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "a-trous levels (%d launches/frame)" % at_launches,
                      "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
-                     "bytes_per_launch": int(at_bytes / max(1, at_launches)), "ms_per_launch": round(at_ms_per_frame / max(1, at_launches), 5),
-                     "peak_source": peak_src},
-        "frame_roofline": {"algorithmic_bytes": int(frame_bytes), "achieved": round(frame_bytes / (ms_max / K * 1e-3) / 1e9, 1),
-                           "frac": round(frame_bytes / (ms_max / K * 1e-3) / 1e9 / peak, 4), "unit": "GB/s"},
-        "stage_ms_per_frame": {k: round(prof[k] / max(1, prof["frames"]), 5) for k in ("temporal_ms", "variance_ms", "atrous_ms")},
+                     "bytes_per_launch": int(at_bytes / max(1, at_launches)), "ms_per_launch": round(at_ms / max(1, at_launches), 5),
+                     "peak_source": peak_src,
+                     "note": "the level is bound by the FP32 pipe / register-file operand bandwidth, not by HBM (DESIGN.md section 6); frac is algorithmic bytes over the HBM peak as the contract asks"},
+        "frame_roofline": {"algorithmic_bytes": int(frame_bytes), "achieved": round(frame_bytes / (ms_per_step * 1e-3) / 1e9, 1),
+                           "frac": round(frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4), "unit": "GB/s"},
+        "stage_ms_per_frame": stage,
+        "taa": {"ms_per_frame": round(taa_ms, 5), "frac_of_hbm_peak": round(bpp["taa"] * W * H / (taa_ms * 1e-3) / 1e9 / peak, 4),
+                "bytes_per_px": bpp["taa"], "what": "svgf_taa (reference src/Filter.cuh:288-357), not part of `value`"},
+        "general_case": general,
         "clocks": sampler.result(),
     }
+    if streams_rec:
+        line["streams_1080p"] = streams_rec
+    if bands_rec:
+        line["bands"] = bands_rec
     return line
 
 
 def run_bands(args, rank, world, local):
-    """--mode bands (BASELINE configs[3]): ONE frame stream, every frame split into `world` horizontal bands with
-    per-level halo rows exchanged between neighbouring ranks (NCCL send/recv over NVLink); strong scaling."""
-    import torch
-    from svgf_b200 import synth
-    from svgf_b200.bands import balanced_bounds, make_gpu_banded_filter, required_apron
-    from svgf_b200.filter import GBuffer
+    """--mode bands (BASELINE configs[3]): ONE frame stream, every frame split into `world` horizontal bands (native band
+    driver, include/svgf_band.h); strong scaling."""
     W, H = WORKLOADS[args.workload]
-    dev = torch.device("cuda", local)
-    K, Wm = args.steps, args.warmup
-    R = K + Wm
-    # auto (-1): when the bands are tall, let a wide apron absorb every level's halo (one overlapped state exchange per
-    # frame, no per-level exchange: the exchanges are latency- and host-bound, redundant rows are cheap); short bands keep
-    # the 32-row apron and exchange before levels 3 and 4
-    if args.band_exchange_from < 0:
-        wide = required_apron(args.levels, args.levels, args.band_max_motion)
-        wide = (wide + 7) // 8 * 8
-        if H // world >= 4 * wide:
-            args.band_exchange_from, args.band_apron = args.levels, max(args.band_apron, wide)
-        else:
-            args.band_exchange_from = min(3, args.levels)
-    L = min(args.band_exchange_from, args.levels)
-    cdt = torch.float16 if args.storage == "f16" else torch.float32
-    # every rank generates the full frames procedurally on its own GPU and keeps only its local rows (band + aprons)
-    full_g, full_c = GBuffer(W, H, dev), torch.empty(H, W, 4, dtype=cdt, device=dev)
-    bounds = None
-    if args.band_balance and world > 1:
-        # equal estimated work per band: background pixels (linear depth 0) are passed through by the a-trous levels
-        synth.frame_device(full_g, full_c, 0, seed=0)
-        live = (full_g.motion[..., 2] != 0).float().mean(dim=1).cpu().numpy()
-        bounds = balanced_bounds(live + args.band_bg_cost * (1.0 - live), world, min_rows=args.band_apron)
-    bf = make_gpu_banded_filter(W, H, rank, world, dev, storage=args.storage, levels=args.levels, apron=args.band_apron,
-                                exchange_from_level=L, max_motion_rows=args.band_max_motion, overlap_state=bool(args.band_overlap_state),
-                                bounds=bounds)
-    if args.band_dry_run:
-        import svgf_b200.bands as _bands
-        _bands.post_exchange = lambda *a_, **k_: []
-    f, band = bf.f, bf.band
-    Hl = band.local_height
-    ring_g = [GBuffer(W, Hl, dev) for _ in range(R)]
-    ring_c = [torch.empty(Hl, W, 4, dtype=cdt, device=dev) for _ in range(R)]
-    for t in range(R):
-        synth.frame_device(full_g, full_c, t, seed=0)
-        sl = slice(band.ly0, band.ly1)
-        ring_g[t].normal.copy_(full_g.normal[sl]); ring_g[t].uv.copy_(full_g.uv[sl]); ring_g[t].motion.copy_(full_g.motion[sl])
-        ring_c[t].copy_(full_c[sl])
-    del full_g, full_c
-    torch.cuda.synchronize()
-    stream = torch.cuda.current_stream(dev)
-    f.Reset()
-
-    def step(t):
-        P = f.PingPongInx
-        f.Framebuffer[P], f.RenderBuffer[P] = ring_g[t], ring_c[t]      # inputs are consumed in place, no copies
-        bf.Filter()
-        bf.EndFrame()
-
-    for t in range(Wm):
-        step(t)
-    barrier(world)
-    sampler = ClockSampler(physical_gpu_index(local))
-    sampler.start()
-    launches0 = f.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for t in range(Wm, Wm + K):
-        step(t)
-    bf.drain()                      # a state exchange posted under the last frame's levels completes inside the timed region
-    e1.record(stream)
-    barrier(world)
-    sampler.stop_flag = True
-    ms_max = max_over_ranks(e0.elapsed_time(e1), world)
-    # per-rank time: with --band-dry-run (no exchanges, wrong pixels) the ranks are independent and this is each band's own
-    # compute + host cost, i.e. the load balance; otherwise neighbours wait for each other and the values converge
-    ms_by_rank = all_ranks(e0.elapsed_time(e1) / K, world)
-    launches = sum_over_ranks(f.launches - launches0, world)
-    all_rows = [int(v) for v in all_ranks(float(Hl), world)]
-    sampler.join()
+    rec = run_band_frames(args, rank, world, local, W, H, K=args.steps, Wm=max(4, args.warmup), check_frames=args.band_check_frames)
     if rank != 0:
         return None
-    peak, peak_src = measured_peaks()
-    bpp = BYTES_PER_PX[args.storage]
-    frame_bytes = (bpp["temporal"] + bpp["variance"] + bpp["atrous_level"] * args.levels + (bpp["atrous_hist"] if args.levels else 0)) * W * H
-    halo_rows = sum(2 << i for i in range(L, args.levels))
-    halo_bytes = 2 * (world - 1) * (halo_rows * W * OUT_BYTES_PER_PX[args.storage] + bf.state_apron * W * (OUT_BYTES_PER_PX[args.storage] * 3 // 2 + 1))
-    value = W * H * K / (ms_max * 1e-3) / 1e9
-    return {
-        "metric": "svgf_frame_throughput", "value": round(value, 4), "unit": "Gpix/s", "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": round(ms_max / K, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 compute, %s storage" % ("fp16" if args.storage == "f16" else "fp32"), "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[3]: {W}x{H} frames in {world} horizontal band(s), temporal + variance + {args.levels} "
-                               f"a-trous levels, halo exchange (NCCL send/recv) before levels >= {L}, state exchange "
-                               f"{'overlapped with levels 1..' if args.band_overlap_state else 'at frame start'}", "width": W, "height": H,
-                   "atrous_levels": args.levels, "storage": args.storage, "band_rows": band.y1 - band.y0, "apron_rows": bf.apron,
-                   "band_bounds": bounds, "exchange_from_level": L, "overlap_state": bool(args.band_overlap_state), "exchanges_per_frame": 1 + args.levels - L, "local_rows_by_rank": all_rows,
-                   "ms_per_step_by_rank": [round(v, 4) for v in ms_by_rank], "dry_run_no_exchange": bool(args.band_dry_run),
-                   "halo_bytes_per_frame_all_ranks": int(halo_bytes),
-                   "l2": "every step reads a fresh frame"},
-        "gpu_launches": int(launches),
-        "frame_roofline": {"algorithmic_bytes": int(frame_bytes), "achieved": round(frame_bytes / (ms_max / K * 1e-3) / 1e9, 1),
-                           "frac_of_n_gpu_peak": round(frame_bytes / (ms_max / K * 1e-3) / 1e9 / (peak * world), 4), "unit": "GB/s",
-                           "peak_source": peak_src},
-        "clocks": sampler.result(),
-    }
+    cfg = base_config(W, H, args.levels, args.storage)
+    cfg["workload"] = rec.pop("workload")
+    for k in ("band_bounds", "local_rows_by_rank", "ms_per_step_by_rank", "bit_identical_to_one_gpu", "checked_frames", "mismatching_bytes"):
+        cfg[k] = rec.pop(k)
+    return {"metric": "svgf_frame_throughput", "value": rec["value"], "unit": "Gpix/s", "n_gpus": world, "steps": rec["steps"], "warmup": rec["warmup"],
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 compute, %s storage" % ("fp16" if args.storage == "f16" else "fp32"), "data": "synthetic", "config": cfg,
+            "gpu_launches": rec["gpu_launches"], "frame_roofline": {"frac_of_n_gpu_peak": rec["frac_of_n_gpu_hbm_peak"]}}
 
 
-def cpu_baseline(args):
-    """The scalar oracle on the host cores, on a bounded sample of the workload (rank 0, N = 1)."""
+def oracle_band_sample(args, with_parity):
+    """The scalar oracle on the host cores, on a bounded sample of the workload (rank 0, N = 1): the middle band of the
+    frames, full width.  with_parity: the CUDA path filters the same band from the same state (teacher-forced: every
+    frame starts from the oracle's buffers) and the worst differences over the timed frames are reported."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
-    from oracle_lib import OracleFilter, oracle
+    from oracle_lib import OracleFilter, oracle, reference_defaults
     from svgf_b200 import synth
     W, H = WORKLOADS[args.workload]
-    # bounded sample: a horizontal band of the frame (full width) so that ~4 warm + 2 timed frames stay within ~20 s
     Hs = max(64, min(H, int(args.cpu_budget_px / W)))
     y0 = (H - Hs) // 2
-    o = OracleFilter(W, Hs, storage=args.storage)
-    o.params.atrous_iterations = args.levels
+    o = OracleFilter(W, Hs, storage=args.storage, params=reference_defaults(args.levels))
     o.Reset()
+    f = None
+    if with_parity:
+        import torch
+        from common import half_ulp_diff
+        from gpu_util import load_state_from_oracle, npy
+        from svgf_b200 import SvgfFilter
+        f = SvgfFilter(W, Hs, storage=args.storage)
+        f.SpatialFilterSteps = args.levels
+        f.Reset()
     n_warm, n_timed = 4, 2
     t_acc = 0.0
+    par = {"max_rel_err_rgb": 0.0, "max_rel_err_variance": 0.0, "max_abs_err": 0.0, "history_mismatches": 0, "moments_mismatches": 0,
+           "max_fp16_ulps": 0, "fraction_differing": 0.0, "frames_compared": 0}
     for t in range(n_warm + n_timed):
         o.set_inputs(synth.frame_host(W, H, t, storage=args.storage, rows=(y0, y0 + Hs)))
+        if f is not None:
+            load_state_from_oracle(f, o)
         t0 = time.perf_counter()
         o.Filter()
         if t >= n_warm:
             t_acc += time.perf_counter() - t0
+        if f is not None:
+            f.Filter()
+            P = o.PingPongInx
+            got, want = npy(f.FilterBuffer[0]), o.FilterBuffer[0]
+            d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+            w64 = np.abs(want.astype(np.float64))
+            par["max_rel_err_rgb"] = max(par["max_rel_err_rgb"], float((d[..., :3] / np.maximum(w64[..., :3], 1e-2)).max()))
+            par["max_rel_err_variance"] = max(par["max_rel_err_variance"], float((d[..., 3] / np.maximum(w64[..., 3], 2.5e-3)).max()))
+            par["max_abs_err"] = max(par["max_abs_err"], float(d.max()))
+            par["history_mismatches"] += int((npy(f.HistoryLengthBuffer) != o.HistoryLengthBuffer).sum())
+            par["moments_mismatches"] += int((npy(f.MomentsBuffer[P]).view(np.uint8) != o.MomentsBuffer[P].view(np.uint8)).sum())
+            if args.storage == "f16":
+                u = half_ulp_diff(got, want)
+                par["max_fp16_ulps"] = max(par["max_fp16_ulps"], int(u.max()))
+                par["fraction_differing"] = max(par["fraction_differing"], float((u > 0).mean()))
+            else:
+                par["fraction_differing"] = max(par["fraction_differing"], float((d > 0).mean()))
+            par["frames_compared"] += 1
         o.EndFrame()
+    if f is not None:
+        f.close()
     cores = oracle().svgf_oracle_get_threads()
-    return {"value": round(W * Hs * n_timed / t_acc / 1e9, 6), "unit": "Gpix/s", "cores": cores, "kind": "port",
-            "sample": f"{n_timed} steady-state frames (after {n_warm} warm-up frames) of the middle {W}x{Hs} band of the {W}x{H} sequence, "
-                      f"scalar C++ oracle, OpenMP over rows", "ms_per_frame_sample": round(t_acc / n_timed * 1e3, 1)}
+    cb = {"value": round(W * Hs * n_timed / t_acc / 1e9, 6), "unit": "Gpix/s", "cores": cores, "kind": "port",
+          "sample": f"{n_timed} steady-state frames (after {n_warm} warm-up frames) of the middle {W}x{Hs} band of the {W}x{H} sequence, "
+                    f"scalar C++ oracle, OpenMP over rows", "ms_per_frame_sample": round(t_acc / n_timed * 1e3, 1)}
+    if f is None:
+        return cb, None
+    par.update({"vs": "oracle/svgf_oracle.cpp (scalar restatement of src/Filter.cuh:359-624)",
+                "sample": f"frames 0..{n_warm + n_timed - 1} of the middle {W}x{Hs} band, every frame started from the oracle's state (teacher-forced), "
+                          f"result after {args.levels} a-trous levels",
+                "bar": ("fp16 storage: every value within 2 fp16 ulps or 1e-4 absolute" if args.storage == "f16" else "fp32 storage: max relative error 1e-4 (floors 1e-2 radiance, 2.5e-3 variance)"),
+                "full_report": "profiles/parity_r02.json (tools/parity_report.py: configs 1-3, both storages, teacher-forced and free-running)"})
+    for k in ("max_rel_err_rgb", "max_rel_err_variance", "max_abs_err", "fraction_differing"):
+        par[k] = float(f"{par[k]:.3e}")
+    return cb, par
 
 
 def run_reference(args, rank, world, local):
     """--impl reference: the reference's own Filter.cuh kernels (oracle/_ref, patched for compilation only) on
-    this GPU when the .so exists, else the scalar oracle port on the host cores."""
+    this GPU when the .so exists, else the scalar oracle port on the host cores.  Nothing of the product is on this path:
+    parameters are the reference's literals, inputs come from the generator library (libsvgf_synth.so) only."""
     if rank != 0:
         return None
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     W, H = WORKLOADS[args.workload]
-    import numpy as np
     from oracle_lib import RefKernels, RefParams, ref, ref_available
-    from svgf_b200 import _lib as L
     # n_gpus is the launch's N (the contract's key); the reference has no multi-GPU path, so one GPU does the work
     base = {"impl": "reference", "metric": "svgf_frame_throughput", "unit": "Gpix/s", "n_gpus": max(1, world), "gpus_used": 1, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[2]: {W}x{H} camera-pan sequence, temporal + variance + {args.levels} a-trous levels",
-                       "width": W, "height": H, "atrous_levels": args.levels, "storage": "f16"}}
+            "config": base_config(W, H, args.levels, "f16")}
     import torch as _torch
     if not ref_available() or args.storage != "f16" or not _torch.cuda.is_available():
-        cb = cpu_baseline(args)
+        cb, _ = oracle_band_sample(args, with_parity=False)
         base.update({"value": cb["value"], "ms_per_step": cb["ms_per_frame_sample"], "dtype": "f32/f64 compute, fp16 storage",
                      "cpu_baseline": cb, "gpu_launches": 0,
                      "e2e": {"value": cb["value"], "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return base
     import torch
-    from svgf_b200 import synth
-    from svgf_b200.filter import GBuffer
     dev = torch.device("cuda", local)
-    p = L.default_params()
-    p.atrous_iterations = args.levels
-    rp = RefParams.from_svgf(p, moments_quirk=0)
+    # src/App.h:109-114, SpatialFilterSteps = BASELINE's level count
+    rp = RefParams(args.levels, 0.8, 0.9, 24, 10.0, 128.0, 0)
     r = RefKernels(W, H)
     K, Wm = args.steps, args.warmup
     R = min(K + Wm, args.ring)
     ring = FrameRing(W, H, R, "f16", seed=0, device=dev)
     D2D = 3
     tot_ms = 0.0
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ms1 = C.c_float()
     for t in range(Wm + K):
         P = ref().svgf_ref_get_ping_pong(r.ctx)
@@ -503,9 +775,9 @@ def run_reference(args, rank, world, local):
     value = W * H * K / (tot_ms * 1e-3) / 1e9
     # end to end with host buffers
     host = []
+    ring.restore_colour(0, 4)
     for t in range(4):
         g = ring.gbuf[t % R]
-        synth.frame_device(g, ring.colour[t % R], t, seed=0)
         host.append({"normal": g.normal.cpu().pin_memory(), "uv": g.uv.cpu().pin_memory(), "motion": g.motion.cpu().pin_memory(),
                      "colour": ring.colour[t % R].cpu().pin_memory()})
     result = torch.empty(H, W, 4, dtype=torch.float16).pin_memory()
@@ -531,7 +803,7 @@ def run_reference(args, rank, world, local):
                                    "and launched like src/App.cu:469-514 on this B200; every step of the workload"},
         "e2e": {"value": round(e2e_value, 4), "unit": "Gpix/s", "h2d_bytes_per_step": IN_BYTES_PER_PX["f16"] * W * H,
                 "d2h_bytes_per_step": OUT_BYTES_PER_PX["f16"] * W * H, "ms_per_step": round(t_e2e / Ke * 1e3, 4),
-                "api": "reference kernels behind host buffers (cudaArray uploads + stages + result download)"},
+                "api": "reference kernels behind host buffers (cudaArray uploads + stages + result download, synchronous like the reference's frame loop)"},
     })
     r.close()
     return base
@@ -547,20 +819,20 @@ def main():
     ap.add_argument("--size", default=None, help="WxH override of --workload (diagnostics; e.g. 7680x2240 = one band of an 8K frame)")
     ap.add_argument("--storage", default="f16", choices=["f16", "f32"])
     ap.add_argument("--levels", type=int, default=5)
-    ap.add_argument("--ring", type=int, default=200, help="max distinct frames kept resident in HBM")
+    ap.add_argument("--ring", type=int, default=200, help="max distinct frames kept resident in HBM (must hold warmup + steps)")
+    ap.add_argument("--max-repeats", type=int, default=12, help="upper bound on repeats of the K-step timed region (each repeat re-warms the sequence)")
     ap.add_argument("--e2e-steps", type=int, default=48)
-    ap.add_argument("--cpu-budget-px", type=float, default=1.6e6, help="pixels per frame of the CPU-baseline sample")
+    ap.add_argument("--cpu-budget-px", type=float, default=1.6e6, help="pixels per frame of the CPU-baseline / parity sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="only the headline measurement and e2e (no general case, PCIe ceiling, 1080p streams, bands)")
+    ap.add_argument("--stream-frames", type=int, default=20, help="timed frames per stream of the 64 x 1080p record")
+    ap.add_argument("--band-frames", type=int, default=24, help="timed 8K frames of the `bands` record (N > 1)")
+    ap.add_argument("--band-check-frames", type=int, default=3, help="--mode bands: frames compared bit for bit with the whole frame on rank 0")
     ap.add_argument("--prefilter", type=int, default=0, help="svgf_params.variance_prefilter (1 = 3x3 Gaussian, not in the reference)")
     ap.add_argument("--reproj", type=int, default=0, help="svgf_params.reproj_mode (1 = bilinear 2x2, not in the reference)")
-    ap.add_argument("--flags", type=int, default=0, help="svgf_params.flags for A/B runs (8 = no uniform-normal tile shortcut)")
-    ap.add_argument("--band-dry-run", type=int, default=0, help="--mode bands diagnostics: 1 = skip every exchange (pixels near band edges are wrong); shows per-rank load")
-    ap.add_argument("--band-balance", type=int, default=1, help="--mode bands: 1 = band heights balanced by estimated work (background rows are cheap), 0 = equal heights")
-    ap.add_argument("--band-bg-cost", type=float, default=0.45, help="--mode bands: cost of a background pixel relative to a filtered one")
-    ap.add_argument("--band-apron", type=int, default=32, help="--mode bands: apron rows on each side of a band")
-    ap.add_argument("--band-exchange-from", type=int, default=-1, help="--mode bands: first a-trous level that exchanges its halo (lower levels recompute it in the apron); -1 = choose from the band height")
-    ap.add_argument("--band-max-motion", type=int, default=8, help="--mode bands: vertical reach (rows) of the temporal gather covered by the apron")
-    ap.add_argument("--band-overlap-state", type=int, default=1, help="--mode bands: 1 = post the previous-frame state exchange under levels 1..N-1")
+    ap.add_argument("--flags", type=int, default=0, help="svgf_params.flags for A/B runs (8 = no uniform-normal tile shortcut, 32 = no staged levels)")
+    ap.add_argument("--band-balance", type=int, default=1, help="bands: 1 = band heights balanced by estimated work (background rows are cheap), 0 = equal heights")
+    ap.add_argument("--band-bg-cost", type=float, default=0.45, help="bands: cost of a background pixel relative to a filtered one")
     ap.add_argument("--mode", default="streams", choices=["streams", "bands"],
                     help="multi-GPU sharding: independent frame streams per GPU (weak scaling, default) or one frame in "
                          "horizontal bands with per-level halo exchange (strong scaling; BASELINE configs[3], use --workload 8k)")
@@ -571,8 +843,13 @@ def main():
         args.workload = args.size
     if args.warmup < 3:
         args.warmup = 3
-    if args.workload == "8k":
-        args.ring = min(args.ring, 48)
+    W, H = WORKLOADS[args.workload]
+    if args.impl == "ours" and args.mode == "streams":
+        # the resident ring must hold warmup + steps distinct frames (an 8K frame is 1.3 GB): bound K by what fits ~100 GB
+        fit = int(100e9 // (IN_BYTES_PER_PX[args.storage] * W * H)) - args.warmup
+        if args.steps > fit:
+            args.steps = max(4, fit)
+        args.ring = max(args.ring, args.warmup + args.steps) if args.warmup + args.steps <= fit + args.warmup else args.ring
 
     import __graft_entry__ as g
     if not (os.path.exists(os.path.join(ROOT, "svgf_b200", "libsvgf_b200.so")) and os.path.exists(os.path.join(ROOT, "oracle", "libsvgf_oracle.so"))):
@@ -585,7 +862,9 @@ def main():
     else:
         line = run_ours(args, rank, world, local)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args)
+            cb, par = oracle_band_sample(args, with_parity=True)
+            line["cpu_baseline"] = cb
+            line["parity"] = par
     if rank == 0 and line is not None:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -14,22 +14,27 @@
 // a separate, caller-owned plane: the previous call's output (snapshot semantics, like the history-length plane, D3).
 //
 // Pure streaming pass: 8 B in + 8 B history + 8 B out per pixel (fp16 storage); the nine neighbourhood texels of a pixel
-// are shared with its neighbours through L1.  pow(x, 2) = x * x, pow(x, 0.5) = sqrt, pow(x, 1/2.4) = ex2(lg2(x) / 2.4):
-// MUFU approximations (<= 2^-21 relative) - the result is rounded to the storage format and compared at the parity bar.
+// are shared with its neighbours through L1.  pow(x, 2) = x * x, pow(x, 0.5) = IEEE sqrt; only the final, continuous
+// pow(x, 1/2.4) is ex2(lg2(x) / 2.4) on the MUFU (<= 2^-21 relative).
 #pragma once
 #include "svgf_device.cuh"
 
 namespace svgf {
 
+// The resolve has a DISCONTINUITY: a decoded component that comes out negative makes pow(x, 0.5) NaN and the reference
+// then blacks out the whole pixel (:351).  The YUV matrices are inverses of each other only to ~5e-6, so components that
+// should be 0 land within rounding of it; to take the same side as the scalar restatement everything up to that decision
+// is evaluated un-contracted, in the reference's order, with IEEE square roots.
+__device__ __forceinline__ float taa_dot3(float x, float y, float z, float a, float b, float c) {   // glm::dot: (x*a + y*b) + z*c
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, a), __fmul_rn(y, b)), __fmul_rn(z, c));
+}
 __device__ __forceinline__ float3 taa_encode_pal_yuv(float3 c) {                     // :267-275
-    const float r = c.x * c.x, g = c.y * c.y, b = c.z * c.z;
-    return make_float3((r * 0.299f + g * 0.587f) + b * 0.114f, (r * -0.14713f + g * -0.28886f) + b * 0.436f,
-                       (r * 0.615f + g * -0.51499f) + b * -0.10001f);
+    const float r = __fmul_rn(c.x, c.x), g = __fmul_rn(c.y, c.y), b = __fmul_rn(c.z, c.z);
+    return make_float3(taa_dot3(r, g, b, 0.299f, 0.587f, 0.114f), taa_dot3(r, g, b, -0.14713f, -0.28886f, 0.436f),
+                       taa_dot3(r, g, b, 0.615f, -0.51499f, -0.10001f));
 }
 __device__ __forceinline__ float taa_sqrt(float x) {   // pow(x, 0.5): NaN for x < 0, +0 for -0
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y + 0.0f;
+    return __fadd_rn(__fsqrt_rn(x), 0.0f);
 }
 __device__ __forceinline__ float taa_to_srgb(float c) {                             // :145-148
     const float hi = 1.055f * fast_exp2(fast_log2(fmaxf(c, 1e-30f)) * (1.0f / 2.4f)) - 0.055f;
@@ -57,9 +62,9 @@ taa_kernel(int W, int H, const typename ColourPlane<F32>::texel *__restrict__ fi
     const float4 last = load(history, 1, 1);                                         // :299
     const float4 c0 = load(filtered, 1, 1);                                          // :306
     const float rate = fminf(last.w, 0.5f);                                          // :302
-    float3 aa = make_float3(mix_rn(last.x * last.x, c0.x * c0.x, rate), mix_rn(last.y * last.y, c0.y * c0.y, rate),
-                            mix_rn(last.z * last.z, c0.z * c0.z, rate));             // :308
-    aa = taa_encode_pal_yuv(make_float3(taa_sqrt(aa.x), taa_sqrt(aa.y), taa_sqrt(aa.z)));   // :309,:320
+    float3 aa = make_float3(mix_rn(__fmul_rn(last.x, last.x), __fmul_rn(c0.x, c0.x), rate), mix_rn(__fmul_rn(last.y, last.y), __fmul_rn(c0.y, c0.y), rate),
+                            mix_rn(__fmul_rn(last.z, last.z), __fmul_rn(c0.z, c0.z), rate));             // :308
+    aa = taa_encode_pal_yuv(make_float3(__fsqrt_rn(aa.x), __fsqrt_rn(aa.y), __fsqrt_rn(aa.z)));   // :309,:320
     // plus-shaped box (in0..in4), then the diagonal texels (in5..in8) folded in: :331-336
     const float3 e0 = taa_encode_pal_yuv(make_float3(c0.x, c0.y, c0.z));
     float3 mn = e0, mx = e0;
@@ -72,11 +77,13 @@ taa_kernel(int W, int H, const typename ColourPlane<F32>::texel *__restrict__ fi
     fold(2, 1, mn, mx); fold(0, 1, mn, mx); fold(1, 2, mn, mx); fold(1, 0, mn, mx);
     float3 mn2 = mn, mx2 = mx;
     fold(2, 2, mn2, mx2); fold(0, 2, mn2, mx2); fold(2, 0, mn2, mx2); fold(0, 0, mn2, mx2);
-    mn = make_float3(0.5f * mn.x + 0.5f * mn2.x, 0.5f * mn.y + 0.5f * mn2.y, 0.5f * mn.z + 0.5f * mn2.z);   // exact halves: one rounding, like the reference's FP64 mix
-    mx = make_float3(0.5f * mx.x + 0.5f * mx2.x, 0.5f * mx.y + 0.5f * mx2.y, 0.5f * mx.z + 0.5f * mx2.z);
+    auto half_mix = [](float x, float y) { return __fadd_rn(0.5f * x, 0.5f * y); };   // exact halves, one rounding: == the reference's FP64 mix
+    mn = make_float3(half_mix(mn.x, mn2.x), half_mix(mn.y, mn2.y), half_mix(mn.z, mn2.z));
+    mx = make_float3(half_mix(mx.x, mx2.x), half_mix(mx.y, mx2.y), half_mix(mx.z, mx2.z));
     aa = make_float3(fminf(fmaxf(aa.x, mn.x), mx.x), fminf(fmaxf(aa.y, mn.y), mx.y), fminf(fmaxf(aa.z, mn.z), mx.z));   // :339
     // decodePalYuv :277-285
-    float3 rgb = make_float3(aa.x + aa.z * 1.13983f, (aa.x + aa.y * -0.39465f) + aa.z * -0.58060f, aa.x + aa.y * 2.03211f);
+    float3 rgb = make_float3(taa_dot3(aa.x, aa.y, aa.z, 1.0f, 0.0f, 1.13983f), taa_dot3(aa.x, aa.y, aa.z, 1.0f, -0.39465f, -0.58060f),
+                             taa_dot3(aa.x, aa.y, aa.z, 1.0f, 2.03211f, 0.0f));
     rgb = make_float3(taa_sqrt(rgb.x), taa_sqrt(rgb.y), taa_sqrt(rgb.z));
     if (rgb.x != rgb.x || rgb.y != rgb.y || rgb.z != rgb.z) rgb = make_float3(0.f, 0.f, 0.f);   // :351
     const float4 o = make_float4(taa_to_srgb(rgb.x), taa_to_srgb(rgb.y), taa_to_srgb(rgb.z), 1.0f);   // :353

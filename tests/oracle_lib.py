@@ -37,6 +37,18 @@ def oracle():
     return _o
 
 
+def reference_defaults(levels=5):
+    """svgf_params filled LITERALLY from the reference's members (src/App.h:109-114; SpatialFilterSteps is 3 there, BASELINE.json
+    measures 5) with the added knobs neutral - without loading the product library (bench.py's reference arm must not map it)."""
+    p = SvgfParams()
+    p.history_cap, p.depth_threshold, p.normal_threshold, p.phi_colour, p.phi_normal = 24, 0.8, 0.9, 10.0, 128.0
+    p.atrous_iterations = levels
+    p.phi_depth, p.alpha_min, p.moments_alpha_min = 1.0, 0.0, 0.0
+    p.mesh_id_mode = p.reproj_mode = p.variance_prefilter = 0
+    p.flags = 0
+    return p
+
+
 def np_gbuf(normal, uv, motion):
     g = SvgfGBuffer()
     g.position_id = None
@@ -56,7 +68,6 @@ class OracleFilter:
     """numpy twin of svgf_b200.filter.SvgfFilter running the scalar oracle: same member names, same call order."""
 
     def __init__(self, width, height, storage="f16", params=None):
-        from svgf_b200._lib import default_params
         self.Width, self.Height = width, height
         self.storage = 0 if storage == "f16" else 1
         cdt = np.float16 if storage == "f16" else np.float32
@@ -69,7 +80,7 @@ class OracleFilter:
         self.FilterBuffer = [np.zeros((H, W, 4), cdt) for _ in range(2)]
         self.HistoryLengthBuffer = np.zeros((H, W), np.uint8)
         self.PingPongInx = 0
-        self.params = params if params is not None else default_params()
+        self.params = params if params is not None else reference_defaults()
 
     def gbuf(self, k):
         return np_gbuf(self.normal[k], self.uv[k], self.motion[k])

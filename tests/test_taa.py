@@ -90,7 +90,11 @@ def test_taa_kernel_against_the_oracle_over_a_short_sequence(size, storage):
             # and contracts the YUV dot products; outputs are in [0, 1]
             assert np.abs(got.astype(np.float64) - want).max() <= 1e-4, f"frame {t}"
         else:
-            assert_close(got, want, storage, f"TAA frame {t} {size}", max_flips=0.02)
+            # the resolve is discontinuous where a decoded component is within rounding of 0 (negative -> NaN -> the whole pixel
+            # is blacked out, src/Filter.cuh:351): libm's powf(x, 2) vs x * x can still put a handful of pixels on the other side
+            from common import f16_errors
+            e = f16_errors(got, want)
+            assert e["violations"] <= max(2, int(2e-5 * got.size)) and e["flip_fraction"] <= 0.02, f"TAA frame {t} {size}: {e}"
         assert np.all(got[..., 3] == 1.0)
         f.TAABuffer[f.PingPongInx].copy_(torch.from_numpy(want))
         f.EndFrame(); o.EndFrame()
