@@ -72,6 +72,12 @@ typedef enum svgf_reproj_mode { SVGF_REPROJ_NEAREST_TRUNC = 0, SVGF_REPROJ_BILIN
  * clamped to the image; everything else is unchanged. */
 typedef enum svgf_variance_prefilter { SVGF_VARIANCE_PREFILTER_NONE = 0, SVGF_VARIANCE_PREFILTER_GAUSS3 = 1 } svgf_variance_prefilter;
 
+/* Depth consistency test of the reprojection.  ABSOLUTE is what the reference does (src/Filter.cuh:242: |z_prev - z_cur| >
+ * DepthThreshold, world units).  RELATIVE is the form the reference left commented out one line above (src/Filter.cuh:241):
+ * |z_prev - z_cur| / (dz_cur + 1e-2) > DepthThreshold with dz_cur the current pixel's depth derivative (motion_depth.w; 0 for
+ * background) - the threshold then scales with the slope of the surface. */
+typedef enum svgf_depth_test_mode { SVGF_DEPTH_TEST_ABSOLUTE = 0, SVGF_DEPTH_TEST_RELATIVE = 1 } svgf_depth_test_mode;
+
 /* svgf_params.flags */
 #define SVGF_FLAG_NONE 0u
 /* svgf_frame only: do not reuse the compact guide plane cached from the previous svgf_frame call for the
@@ -138,6 +144,7 @@ typedef struct svgf_params {
     int32_t reproj_mode;         /* svgf_reproj_mode */
     int32_t variance_prefilter;  /* svgf_variance_prefilter */
     uint32_t flags;              /* SVGF_FLAG_* */
+    int32_t depth_test_mode;     /* svgf_depth_test_mode */
 } svgf_params;
 
 /* One G-buffer = the reference's `cudaFramebuffer` (src/App.h:41-44; attachment order src/App.h:33-39).  Each plane is either
@@ -225,6 +232,17 @@ svgf_status svgf_frame(svgf_ctx *ctx, const svgf_params *params, const svgf_gbuf
  * reads texels other threads may already have overwritten (src/Filter.cuh:299 vs :355); here the two must be distinct
  * planes that the caller swaps every frame (snapshot semantics). */
 svgf_status svgf_taa(svgf_ctx *ctx, const void *filtered, const void *taa_history, void *taa_out, void *stream);
+
+/* Albedo demodulation, the step of the SVGF paper the reference leaves out (README.md:14,172-174): filter the untextured
+ * illumination so that textures are not blurred.  Two element-wise passes around the frame, both optional (nothing else
+ * in the path changes, so without them the reference's behaviour is untouched):
+ *   svgf_demodulate : colour.rgb <- colour.rgb / max(albedo.rgb, 1e-3)   before svgf_frame / svgf_temporal (in place; w kept)
+ *   svgf_remodulate : out.rgb    <- filtered.rgb * albedo.rgb            after the last a-trous level (w copied)
+ * `albedo` is a plane in the storage texel format, rgb = surface albedo of the pixel (w ignored).  IEEE division and
+ * multiplication, one rounding each, then the storage format's rounding.  Like every plane of the reference the
+ * illumination is clamped to [0,1] by the passes in between (src/Filter.cuh:63-83): scale HDR input accordingly. */
+svgf_status svgf_demodulate(svgf_ctx *ctx, const void *albedo, void *colour, void *stream);
+svgf_status svgf_remodulate(svgf_ctx *ctx, const void *albedo, const void *filtered, void *out, void *stream);
 
 /* The context caches a compact "guide" plane (depth, depth derivative, normal, mesh id: 22 B/px) per
  * G-buffer, keyed by the three plane pointers and pitches of the svgf_gbuffer: svgf_temporal / svgf_frame build it for the current

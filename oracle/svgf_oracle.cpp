@@ -183,6 +183,7 @@ int check_common(const svgf_params *p, int W, int H, int storage) {
     if (p->history_cap < 1 || p->history_cap > 255) return SVGF_INVALID_ARG;  // D9
     if (p->atrous_iterations < 0 || p->atrous_iterations > 10) return SVGF_INVALID_ARG;
     if (p->reproj_mode != SVGF_REPROJ_NEAREST_TRUNC && p->reproj_mode != SVGF_REPROJ_BILINEAR) return SVGF_UNSUPPORTED;
+    if (p->depth_test_mode != SVGF_DEPTH_TEST_ABSOLUTE && p->depth_test_mode != SVGF_DEPTH_TEST_RELATIVE) return SVGF_INVALID_ARG;
     if (p->variance_prefilter != SVGF_VARIANCE_PREFILTER_NONE && p->variance_prefilter != SVGF_VARIANCE_PREFILTER_GAUSS3)
         return SVGF_UNSUPPORTED;
     return SVGF_OK;
@@ -207,7 +208,9 @@ void temporal(const svgf_params &P, int W, int H, const GBuf &cur, const GBuf &p
                 if (qx < 0 || qx >= W || qy < 0 || qy >= H) return false;            // :235
                 const V2 dc = cur.depth(x, y);                                       // :239
                 const V2 dp = prev.depth(qx, qy);                                    // :240
-                if (fabsf(dp.x - dc.x) > P.depth_threshold) return false;            // :242
+                if (P.depth_test_mode == SVGF_DEPTH_TEST_RELATIVE) {
+                    if (fabsf(dp.x - dc.x) / (dc.y + 1e-2f) > P.depth_threshold) return false;   // :241, the commented-out form
+                } else if (fabsf(dp.x - dc.x) > P.depth_threshold) return false;     // :242
                 if (cur.mesh_id(x, y, P.mesh_id_mode) != prev.mesh_id(qx, qy, P.mesh_id_mode)) return false;  // :245-247
                 const V3 n0 = cur.nrm(x, y), n1 = prev.nrm(qx, qy);                  // :250-251
                 return !(dot3(n0, n1) < P.normal_threshold);                         // :252
@@ -538,6 +541,34 @@ int svgf_oracle_frame(const svgf_params *p, int W, int H, int storage, const svg
     }
     if (p->atrous_iterations % 2 != 0)  // src/App.cu:510-513
         std::memcpy(b->filter[0], b->filter[1], n * (storage == SVGF_STORE_F32 ? 16 : 8));
+    return SVGF_OK;
+}
+
+// Albedo demodulation / remodulation (include/svgf.h; README.md:172-174: the paper's step the reference leaves out).
+int svgf_oracle_demodulate(int W, int H, int storage, const void *albedo, void *colour) {
+    if (W <= 0 || H <= 0 || !albedo || !colour) return SVGF_INVALID_ARG;
+    for (size_t i = 0; i < (size_t)W * H; i++) {
+        if (storage == SVGF_STORE_F32) {
+            const V4 a = Colour<true>::raw(albedo, i), c = Colour<true>::raw(colour, i);
+            Colour<true>::store_raw(colour, i, {c.x / fmaxf(a.x, 1e-3f), c.y / fmaxf(a.y, 1e-3f), c.z / fmaxf(a.z, 1e-3f), c.w});
+        } else {
+            const V4 a = Colour<false>::raw(albedo, i), c = Colour<false>::raw(colour, i);
+            Colour<false>::store_raw(colour, i, {c.x / fmaxf(a.x, 1e-3f), c.y / fmaxf(a.y, 1e-3f), c.z / fmaxf(a.z, 1e-3f), c.w});
+        }
+    }
+    return SVGF_OK;
+}
+int svgf_oracle_remodulate(int W, int H, int storage, const void *albedo, const void *in, void *out) {
+    if (W <= 0 || H <= 0 || !albedo || !in || !out) return SVGF_INVALID_ARG;
+    for (size_t i = 0; i < (size_t)W * H; i++) {
+        if (storage == SVGF_STORE_F32) {
+            const V4 a = Colour<true>::raw(albedo, i), c = Colour<true>::raw(in, i);
+            Colour<true>::store_raw(out, i, {c.x * a.x, c.y * a.y, c.z * a.z, c.w});
+        } else {
+            const V4 a = Colour<false>::raw(albedo, i), c = Colour<false>::raw(in, i);
+            Colour<false>::store_raw(out, i, {c.x * a.x, c.y * a.y, c.z * a.z, c.w});
+        }
+    }
     return SVGF_OK;
 }
 

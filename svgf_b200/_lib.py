@@ -11,6 +11,7 @@ SYNTH_PATH = os.path.join(_HERE, "libsvgf_synth.so")
 SVGF_OK, SVGF_INVALID_ARG, SVGF_UNSUPPORTED, SVGF_CUDA_ERROR = 0, 1, 2, 3
 SVGF_STORE_F16, SVGF_STORE_F32 = 0, 1
 SVGF_MESH_ID_INTENDED, SVGF_MESH_ID_REFERENCE_VACUOUS = 0, 1
+SVGF_DEPTH_TEST_ABSOLUTE, SVGF_DEPTH_TEST_RELATIVE = 0, 1
 SVGF_FLAG_NO_GUIDE_CACHE, SVGF_FLAG_NO_LEVEL_FUSION, SVGF_FLAG_BASIC_KERNELS, SVGF_FLAG_NO_UNIFORM_TILES = 1, 2, 4, 8
 SVGF_FLAG_FUSE_LEVELS_01 = 16
 SVGF_FLAG_NO_STAGED_LEVELS, SVGF_FLAG_ATROUS_BULK, SVGF_FLAG_ATROUS_STREAM, SVGF_FLAG_NO_DEPENDENT_LAUNCH = 32, 64, 128, 256
@@ -28,7 +29,7 @@ class SvgfParams(C.Structure):
         ("phi_colour", C.c_float), ("phi_normal", C.c_float), ("atrous_iterations", C.c_int32),
         ("phi_depth", C.c_float), ("alpha_min", C.c_float), ("moments_alpha_min", C.c_float),
         ("mesh_id_mode", C.c_int32), ("reproj_mode", C.c_int32), ("variance_prefilter", C.c_int32),
-        ("flags", C.c_uint32),
+        ("flags", C.c_uint32), ("depth_test_mode", C.c_int32),
     ]
 
 
@@ -75,6 +76,8 @@ ABI = [
     ("svgf_frame", C.c_int, [C.c_void_p, C.POINTER(SvgfParams), C.POINTER(SvgfGBuffer * 2), C.POINTER(SvgfFrameBuffers),
                              C.c_void_p]),
     ("svgf_taa", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("svgf_demodulate", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("svgf_remodulate", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("svgf_invalidate_guide", None, [C.c_void_p]),
     ("svgf_profile_begin", C.c_int, [C.c_void_p]),
     ("svgf_profile_end", C.c_int, [C.c_void_p, C.POINTER(C.c_double * 3), C.POINTER(C.c_int)]),

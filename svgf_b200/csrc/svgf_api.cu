@@ -29,6 +29,7 @@ svgf_status check_params(const svgf_params *p) {
     if (!(p->alpha_min >= 0.0f && p->alpha_min <= 1.0f) || !(p->moments_alpha_min >= 0.0f && p->moments_alpha_min <= 1.0f))
         return SVGF_INVALID_ARG;
     if (p->mesh_id_mode != SVGF_MESH_ID_INTENDED && p->mesh_id_mode != SVGF_MESH_ID_REFERENCE_VACUOUS) return SVGF_INVALID_ARG;
+    if (p->depth_test_mode != SVGF_DEPTH_TEST_ABSOLUTE && p->depth_test_mode != SVGF_DEPTH_TEST_RELATIVE) return SVGF_INVALID_ARG;
     if (p->reproj_mode != SVGF_REPROJ_NEAREST_TRUNC && p->reproj_mode != SVGF_REPROJ_BILINEAR) return SVGF_UNSUPPORTED;
     if (p->variance_prefilter != SVGF_VARIANCE_PREFILTER_NONE && p->variance_prefilter != SVGF_VARIANCE_PREFILTER_GAUSS3)
         return SVGF_UNSUPPORTED;
@@ -105,6 +106,7 @@ svgf_status launch_temporal(svgf_ctx *c, const svgf_params *p, const svgf_gbuffe
     a.depth_threshold = p->depth_threshold; a.normal_threshold = p->normal_threshold;
     a.history_cap = p->history_cap; a.alpha_min = p->alpha_min; a.moments_alpha_min = p->moments_alpha_min;
     a.vacuous_mesh_id = (p->mesh_id_mode == SVGF_MESH_ID_REFERENCE_VACUOUS);
+    a.relative_depth = (p->depth_test_mode == SVGF_DEPTH_TEST_RELATIVE);
     a.force_fail = c->force_fail_next ? 1 : 0;
     // previous-frame guide: reuse the plane cached when `prev` was the current G-buffer
     int prev_slot = -1;
@@ -438,6 +440,7 @@ void svgf_default_params(svgf_params *p) {
     p->reproj_mode = SVGF_REPROJ_NEAREST_TRUNC;
     p->variance_prefilter = SVGF_VARIANCE_PREFILTER_NONE;
     p->flags = SVGF_FLAG_NONE;
+    p->depth_test_mode = SVGF_DEPTH_TEST_ABSOLUTE;
 }
 
 svgf_status svgf_create(svgf_ctx **out, int device, int width, int height, svgf_storage storage) {
@@ -649,6 +652,32 @@ svgf_status svgf_taa(svgf_ctx *c, const void *filtered, const void *taa_history,
         taa_kernel<true><<<grid_for(c), 256, 0, s>>>(c->W, c->H, (const float4 *)filtered, (const float4 *)taa_history, (float4 *)taa_out);
     else
         taa_kernel<false><<<grid_for(c), 256, 0, s>>>(c->W, c->H, (const uint2 *)filtered, (const uint2 *)taa_history, (uint2 *)taa_out);
+    c->launches++;
+    SVGF_CUDA(c, cudaGetLastError());
+    return SVGF_OK;
+}
+
+svgf_status svgf_demodulate(svgf_ctx *c, const void *albedo, void *colour, void *stream) {
+    if (!c || !albedo || !colour || albedo == colour) return SVGF_INVALID_ARG;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return SVGF_CUDA_ERROR;
+    const size_t n = (size_t)c->W * c->H;
+    if (c->storage == SVGF_STORE_F32) demodulate_kernel<true><<<c->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(n, (const float4 *)albedo, (float4 *)colour);
+    else demodulate_kernel<false><<<c->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(n, (const uint2 *)albedo, (uint2 *)colour);
+    c->launches++;
+    SVGF_CUDA(c, cudaGetLastError());
+    return SVGF_OK;
+}
+
+svgf_status svgf_remodulate(svgf_ctx *c, const void *albedo, const void *filtered, void *out, void *stream) {
+    if (!c || !albedo || !filtered || !out || albedo == out) return SVGF_INVALID_ARG;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return SVGF_CUDA_ERROR;
+    const size_t n = (size_t)c->W * c->H;
+    if (c->storage == SVGF_STORE_F32)
+        remodulate_kernel<true><<<c->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(n, (const float4 *)albedo, (const float4 *)filtered, (float4 *)out);
+    else
+        remodulate_kernel<false><<<c->num_sms * 8, 256, 0, (cudaStream_t)stream>>>(n, (const uint2 *)albedo, (const uint2 *)filtered, (uint2 *)out);
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
     return SVGF_OK;

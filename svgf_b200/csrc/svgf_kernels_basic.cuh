@@ -43,6 +43,7 @@ struct TemporalArgs {
     int history_cap;
     float alpha_min, moments_alpha_min;
     int vacuous_mesh_id;   // svgf_mesh_id_mode == REFERENCE_VACUOUS
+    int relative_depth;    // svgf_depth_test_mode == RELATIVE (src/Filter.cuh:241)
     int force_fail;        // first frame after svgf_reset: every reprojection fails (D12)
 };
 
@@ -105,7 +106,9 @@ temporal_kernel(TemporalArgs a, GBufView cur, GBufView prev, Guide prev_guide, G
             const GuideTexel pg = make_guide(prev.mot(qx, qy), prev.nrm(qx, qy), prev.uvw(qx, qy));
             pn = pg.n; pmid = pg.mid;
         }
-        bool good = !(fabsf(pn.x - g.n.x) > a.depth_threshold);                // :242
+        const float dzv = fabsf(pn.x - g.n.x);
+        bool good = a.relative_depth ? !(__fdiv_rn(dzv, __fadd_rn(g.dz, 1e-2f)) > a.depth_threshold)      // :241 (commented-out form)
+                                     : !(dzv > a.depth_threshold);                                        // :242
         good = good && (a.vacuous_mesh_id || guide_mesh_id(g.mid) == guide_mesh_id(pmid));  // :245-247
         return good && !(dot3(guide_normal(g.n), guide_normal(pn)) < a.normal_threshold);  // :250-252
     };
@@ -236,6 +239,26 @@ variance_gauss3_kernel(int W, int H, const typename ColourPlane<F32>::texel *__r
         const float col = __fadd_rn(__fadd_rn(0.25f * v[r], 0.5f * v[r + 1]), 0.25f * v[r + 2]);
         const float l = __shfl_up_sync(0xffffffffu, col, 1), rr = __shfl_down_sync(0xffffffffu, col, 1);
         if (lane >= 1 && lane <= 30 && x < W && y < H) out[(size_t)y * W + x] = __fadd_rn(__fadd_rn(0.25f * l, 0.5f * col), 0.25f * rr);
+    }
+}
+
+// ---- albedo demodulation / remodulation (include/svgf.h; the paper's step the reference leaves out, README.md:172-174) ----
+template <bool F32>
+__global__ void __launch_bounds__(256)
+demodulate_kernel(size_t n, const typename ColourPlane<F32>::texel *__restrict__ albedo, typename ColourPlane<F32>::texel *colour) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = ColourPlane<F32>::decode(__ldg(albedo + i)), c = ColourPlane<F32>::decode(colour[i]);
+        colour[i] = ColourPlane<F32>::encode(make_float4(__fdiv_rn(c.x, fmaxf(a.x, 1e-3f)), __fdiv_rn(c.y, fmaxf(a.y, 1e-3f)),
+                                                         __fdiv_rn(c.z, fmaxf(a.z, 1e-3f)), c.w));
+    }
+}
+template <bool F32>
+__global__ void __launch_bounds__(256)
+remodulate_kernel(size_t n, const typename ColourPlane<F32>::texel *__restrict__ albedo, const typename ColourPlane<F32>::texel *__restrict__ in,
+                  typename ColourPlane<F32>::texel *__restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = ColourPlane<F32>::decode(__ldg(albedo + i)), c = ColourPlane<F32>::decode(__ldg(in + i));
+        out[i] = ColourPlane<F32>::encode(make_float4(__fmul_rn(c.x, a.x), __fmul_rn(c.y, a.y), __fmul_rn(c.z, a.z), c.w));
     }
 }
 

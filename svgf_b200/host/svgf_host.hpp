@@ -138,6 +138,14 @@ public:
         const svgf_frame_buffers b = bufs();
         check(svgf_frame(Ctx, &p, g, &b, Stream), "svgf_frame");
     }
+    // application::TAA(), src/App.cu:516-522: FilterBuffer[0] -> TAABuffer[PingPongInx]; the history is the previous frame's
+    // resolve, TAABuffer[1 - PingPongInx] (the reference uses FilterBuffer[1] for both and races on it, include/svgf.h)
+    void TAA() {
+        for (auto &t : TAABuffer)
+            if (!t) t = std::make_shared<buffer>(FilterBuffer[0]->Size);
+        check(svgf_taa(Ctx, FilterBuffer[0]->Data, TAABuffer[1 - PingPongInx]->Data, TAABuffer[PingPongInx]->Data, Stream), "svgf_taa");
+    }
+    std::shared_ptr<buffer> TAABuffer[2];
     // application::EndFrame(), src/App.cu:374
     void EndFrame() { PingPongInx = 1 - PingPongInx; }
 
@@ -148,7 +156,7 @@ public:
         p.atrous_iterations = SpatialFilterSteps; p.depth_threshold = DepthThreshold; p.normal_threshold = NormalThreshold;
         p.history_cap = HistoryLength; p.phi_colour = PhiColour; p.phi_normal = PhiNormal;
         p.mesh_id_mode = MeshIdMode; p.flags = Flags;
-        p.reproj_mode = ReprojMode; p.variance_prefilter = VariancePrefilter;
+        p.reproj_mode = ReprojMode; p.variance_prefilter = VariancePrefilter; p.depth_test_mode = DepthTestMode;
         return p;
     }
     int MeshIdMode = SVGF_MESH_ID_INTENDED;
@@ -156,6 +164,7 @@ public:
     // switches the reference has no counterpart for (include/svgf.h); the defaults are the reference's behaviour
     int ReprojMode = SVGF_REPROJ_NEAREST_TRUNC;
     int VariancePrefilter = SVGF_VARIANCE_PREFILTER_NONE;
+    int DepthTestMode = SVGF_DEPTH_TEST_ABSOLUTE;
 
 private:
     svgf_storage Storage;

@@ -33,6 +33,8 @@ def oracle():
         o.svgf_oracle_atrous_level.argtypes = [P, C.c_int, C.c_int, C.c_int, G, v, v, v, C.c_int]
         o.svgf_oracle_frame.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(SvgfGBuffer * 2), C.POINTER(SvgfFrameBuffers)]
         o.svgf_oracle_taa.argtypes = [C.c_int, C.c_int, C.c_int, v, v, v]
+        o.svgf_oracle_demodulate.argtypes = [C.c_int, C.c_int, C.c_int, v, v]
+        o.svgf_oracle_remodulate.argtypes = [C.c_int, C.c_int, C.c_int, v, v, v]
         _o = o
     return _o
 
@@ -44,7 +46,7 @@ def reference_defaults(levels=5):
     p.history_cap, p.depth_threshold, p.normal_threshold, p.phi_colour, p.phi_normal = 24, 0.8, 0.9, 10.0, 128.0
     p.atrous_iterations = levels
     p.phi_depth, p.alpha_min, p.moments_alpha_min = 1.0, 0.0, 0.0
-    p.mesh_id_mode = p.reproj_mode = p.variance_prefilter = 0
+    p.mesh_id_mode = p.reproj_mode = p.variance_prefilter = p.depth_test_mode = 0
     p.flags = 0
     return p
 

@@ -52,7 +52,11 @@ def temporal(p, cur, prev, prev_col, cur_col, hist, prev_mom):
             def consistent(qx, qy):
                 if not (0 <= qx < W and 0 <= qy < H):
                     return False
-                if abs(depth(prev["motion"], qx, qy)[0] - depth(cur["motion"], x, y)[0]) > p.depth_threshold:
+                dzv = abs(depth(prev["motion"], qx, qy)[0] - depth(cur["motion"], x, y)[0])
+                if getattr(p, "depth_test_mode", 0) == 1:   # SVGF_DEPTH_TEST_RELATIVE, src/Filter.cuh:241
+                    if f32(f32(dzv) / f32(f32(depth(cur["motion"], x, y)[1]) + f32(1e-2))) > p.depth_threshold:
+                        return False
+                elif dzv > p.depth_threshold:
                     return False
                 if p.mesh_id_mode == 0 and int(cur["inst"][y, x]) != int(prev["inst"][qy, qx]):
                     return False
