@@ -249,34 +249,47 @@ class DeviceSequence:
 
 
 def pcie_ceiling(dev, h2d_bytes, d2h_bytes):
-    """Host<->device copy bandwidth of this GPU with both directions busy at once, from pinned memory - what bounds the e2e
-    figure.  Returns GB/s per direction and the time one step's transfers need at those rates."""
+    """Host<->device copy bandwidth of this GPU from pinned memory: each direction alone and both at once.  The ceiling of
+    the e2e figure is the larger of the two directions' transfer times at the ALONE rates (a pipelined frame cannot finish
+    faster than its bigger copy); the concurrent rates show what full-duplex contention costs."""
     import torch
     n = 256 << 20
     hin, hout = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
     din, dout = torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev)
     s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    best = [0.0, 0.0]
-    for it in range(4):
-        torch.cuda.synchronize()
-        with torch.cuda.stream(s1):
-            ev[0].record(s1)
-            for _ in range(3):
-                din.copy_(hin, non_blocking=True)
-            ev[1].record(s1)
-        with torch.cuda.stream(s2):
-            ev[2].record(s2)
-            for _ in range(3):
-                hout.copy_(dout, non_blocking=True)
-            ev[3].record(s2)
-        torch.cuda.synchronize()
-        if it:
-            best[0] = max(best[0], 3 * n / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9)
-            best[1] = max(best[1], 3 * n / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9)
-    step_ms = max(h2d_bytes / (best[0] * 1e9), d2h_bytes / (best[1] * 1e9)) * 1e3
-    return {"h2d_gbs": round(best[0], 2), "d2h_gbs": round(best[1], 2), "ms_per_step_at_ceiling": round(step_ms, 4),
-            "how": "3 x 256 MiB pinned copies per direction, both directions concurrently on two streams, best of 3"}
+
+    def run(do_in, do_out):
+        best = [0.0, 0.0]
+        for it in range(3):
+            torch.cuda.synchronize()
+            if do_in:
+                with torch.cuda.stream(s1):
+                    ev[0].record(s1)
+                    for _ in range(3):
+                        din.copy_(hin, non_blocking=True)
+                    ev[1].record(s1)
+            if do_out:
+                with torch.cuda.stream(s2):
+                    ev[2].record(s2)
+                    for _ in range(3):
+                        hout.copy_(dout, non_blocking=True)
+                    ev[3].record(s2)
+            torch.cuda.synchronize()
+            if it:
+                if do_in:
+                    best[0] = max(best[0], 3 * n / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9)
+                if do_out:
+                    best[1] = max(best[1], 3 * n / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9)
+        return best
+
+    h2d_alone = run(True, False)[0]
+    d2h_alone = run(False, True)[1]
+    both = run(True, True)
+    step_ms = max(h2d_bytes / (h2d_alone * 1e9), d2h_bytes / (d2h_alone * 1e9)) * 1e3
+    return {"h2d_gbs": round(h2d_alone, 2), "d2h_gbs": round(d2h_alone, 2), "h2d_gbs_full_duplex": round(both[0], 2),
+            "d2h_gbs_full_duplex": round(both[1], 2), "ms_per_step_at_ceiling": round(step_ms, 4),
+            "how": "3 x 256 MiB pinned copies per direction, best of 2 after a warm-up; ceiling = the slower direction's bytes per step at its stand-alone rate"}
 
 
 def run_streams_1080p(args, rank, world, local):

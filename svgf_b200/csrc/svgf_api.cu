@@ -648,10 +648,11 @@ svgf_status svgf_taa(svgf_ctx *c, const void *filtered, const void *taa_history,
     DeviceGuard guard(c->device);
     if (!guard.ok) return SVGF_CUDA_ERROR;
     cudaStream_t s = (cudaStream_t)stream;
+    const dim3 grid((c->W + kTaaBW - 1) / kTaaBW, (c->H + kTaaBH - 1) / kTaaBH);
     if (c->storage == SVGF_STORE_F32)
-        taa_kernel<true><<<grid_for(c), 256, 0, s>>>(c->W, c->H, (const float4 *)filtered, (const float4 *)taa_history, (float4 *)taa_out);
+        taa_kernel<true><<<grid, kTaaBW * kTaaBH, 0, s>>>(c->W, c->H, (const float4 *)filtered, (const float4 *)taa_history, (float4 *)taa_out);
     else
-        taa_kernel<false><<<grid_for(c), 256, 0, s>>>(c->W, c->H, (const uint2 *)filtered, (const uint2 *)taa_history, (uint2 *)taa_out);
+        taa_kernel<false><<<grid, kTaaBW * kTaaBH, 0, s>>>(c->W, c->H, (const uint2 *)filtered, (const uint2 *)taa_history, (uint2 *)taa_out);
     c->launches++;
     SVGF_CUDA(c, cudaGetLastError());
     return SVGF_OK;

@@ -13,8 +13,7 @@
 // and application::TAA passes FilterBuffer[1], which the a-trous ping-pong has just used as scratch).  Here the history is
 // a separate, caller-owned plane: the previous call's output (snapshot semantics, like the history-length plane, D3).
 //
-// Pure streaming pass: 8 B in + 8 B history + 8 B out per pixel (fp16 storage); the nine neighbourhood texels of a pixel
-// are shared with its neighbours through L1.  pow(x, 2) = x * x, pow(x, 0.5) = IEEE sqrt; only the final, continuous
+// Streaming pass: 8 B in + 8 B history + 8 B out per pixel (fp16 storage).  pow(x, 2) = x * x, pow(x, 0.5) = IEEE sqrt; only the final, continuous
 // pow(x, 1/2.4) is ex2(lg2(x) / 2.4) on the MUFU (<= 2^-21 relative).
 #pragma once
 #include "svgf_device.cuh"
@@ -46,38 +45,68 @@ __device__ __forceinline__ int taa_texel(float uv, int size) {
     return min(max(t, 0), size - 1);
 }
 
+// Block = 32 x 16 outputs.  The block's source texels (its outputs' floor texels and their neighbours: a 36 x 20 window
+// starting two texels up-left of the block, see taa_texel) are loaded, clamped and PAL-YUV-encoded ONCE into shared memory -
+// each is the neighbour of nine outputs - together with their squared rgb (the blend operand of the centre tap).  A tap
+// that falls outside the window (it cannot, up to float rounding of the uv arithmetic at the clamped image borders, which
+// the window covers) is evaluated from global memory instead, so the window size is an optimisation, not an assumption.
+constexpr int kTaaBW = 32, kTaaBH = 16, kTaaTW = kTaaBW + 4, kTaaTH = kTaaBH + 4;
+
 template <bool F32>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kTaaBW *kTaaBH)
 taa_kernel(int W, int H, const typename ColourPlane<F32>::texel *__restrict__ filtered,
            const typename ColourPlane<F32>::texel *__restrict__ history, typename ColourPlane<F32>::texel *__restrict__ out) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    __shared__ float4 sYuv[kTaaTW * kTaaTH];    // y u v (w unused)
+    __shared__ float4 sSq[kTaaTW * kTaaTH];     // r^2 g^2 b^2 (w unused)
+    const int bx0 = blockIdx.x * kTaaBW, by0 = blockIdx.y * kTaaBH;
+    const int tx0 = max(bx0 - 3, 0), ty0 = max(by0 - 3, 0);      // window origin: floor texels reach x - 2 (one more for rounding slack)
+    for (int i = threadIdx.x; i < kTaaTW * kTaaTH; i += kTaaBW * kTaaBH) {
+        const int ty = i / kTaaTW, tx = i - ty * kTaaTW;
+        const int gx = min(tx0 + tx, W - 1), gy = min(ty0 + ty, H - 1);
+        const float4 c = clamp01(ColourPlane<F32>::decode(__ldg(filtered + (size_t)gy * W + gx)));   // imageLoad :78-83
+        const float r = __fmul_rn(c.x, c.x), g = __fmul_rn(c.y, c.y), b = __fmul_rn(c.z, c.z);
+        sSq[i] = make_float4(r, g, b, 0.f);
+        sYuv[i] = make_float4(taa_dot3(r, g, b, 0.299f, 0.587f, 0.114f), taa_dot3(r, g, b, -0.14713f, -0.28886f, 0.436f),
+                              taa_dot3(r, g, b, 0.615f, -0.51499f, -0.10001f), 0.f);
+    }
+    __syncthreads();
+    const int x = bx0 + (threadIdx.x & (kTaaBW - 1)), y = by0 + threadIdx.x / kTaaBW;
     if (x >= W || y >= H) return;
     const float inv_w = 1.0f / (float)W, inv_h = 1.0f / (float)H;
     const float u = (float)x * inv_w, v = (float)y * inv_h;                          // :296
     const int xs[3] = {taa_texel(u - inv_w, W), taa_texel(u, W), taa_texel(u + inv_w, W)};
     const int ys[3] = {taa_texel(v - inv_h, H), taa_texel(v, H), taa_texel(v + inv_h, H)};
-    auto load = [&](const typename ColourPlane<F32>::texel *p, int ix, int iy) {
-        return clamp01(ColourPlane<F32>::decode(__ldg(p + (size_t)ys[iy] * W + xs[ix])));   // imageLoad :78-83
+    // encoded texel (ix, iy) of the neighbourhood, and optionally its squared rgb
+    auto tap = [&](int ix, int iy, float4 *sq) -> float4 {
+        const int lx = xs[ix] - tx0, ly = ys[iy] - ty0;
+        if (lx >= 0 && lx < kTaaTW && ly >= 0 && ly < kTaaTH) {
+            if (sq) *sq = sSq[ly * kTaaTW + lx];
+            return sYuv[ly * kTaaTW + lx];
+        }
+        const float4 c = clamp01(ColourPlane<F32>::decode(__ldg(filtered + (size_t)ys[iy] * W + xs[ix])));
+        const float r = __fmul_rn(c.x, c.x), g = __fmul_rn(c.y, c.y), b = __fmul_rn(c.z, c.z);
+        if (sq) *sq = make_float4(r, g, b, 0.f);
+        return make_float4(taa_dot3(r, g, b, 0.299f, 0.587f, 0.114f), taa_dot3(r, g, b, -0.14713f, -0.28886f, 0.436f),
+                           taa_dot3(r, g, b, 0.615f, -0.51499f, -0.10001f), 0.f);
     };
-    const float4 last = load(history, 1, 1);                                         // :299
-    const float4 c0 = load(filtered, 1, 1);                                          // :306
+    const float4 last = clamp01(ColourPlane<F32>::decode(__ldg(history + (size_t)ys[1] * W + xs[1])));   // :299
+    float4 c0sq;
+    const float4 e0 = tap(1, 1, &c0sq);                                              // :306
     const float rate = fminf(last.w, 0.5f);                                          // :302
-    float3 aa = make_float3(mix_rn(__fmul_rn(last.x, last.x), __fmul_rn(c0.x, c0.x), rate), mix_rn(__fmul_rn(last.y, last.y), __fmul_rn(c0.y, c0.y), rate),
-                            mix_rn(__fmul_rn(last.z, last.z), __fmul_rn(c0.z, c0.z), rate));             // :308
+    float3 aa = make_float3(mix_rn(__fmul_rn(last.x, last.x), c0sq.x, rate), mix_rn(__fmul_rn(last.y, last.y), c0sq.y, rate),
+                            mix_rn(__fmul_rn(last.z, last.z), c0sq.z, rate));       // :308
     aa = taa_encode_pal_yuv(make_float3(__fsqrt_rn(aa.x), __fsqrt_rn(aa.y), __fsqrt_rn(aa.z)));   // :309,:320
     // plus-shaped box (in0..in4), then the diagonal texels (in5..in8) folded in: :331-336
-    const float3 e0 = taa_encode_pal_yuv(make_float3(c0.x, c0.y, c0.z));
-    float3 mn = e0, mx = e0;
+    float3 mn = make_float3(e0.x, e0.y, e0.z), mx = mn;
     auto fold = [&](int ix, int iy, float3 &lo, float3 &hi) {
-        const float4 c = load(filtered, ix, iy);
-        const float3 e = taa_encode_pal_yuv(make_float3(c.x, c.y, c.z));
+        const float4 e = tap(ix, iy, nullptr);
         lo = make_float3(fminf(lo.x, e.x), fminf(lo.y, e.y), fminf(lo.z, e.z));
         hi = make_float3(fmaxf(hi.x, e.x), fmaxf(hi.y, e.y), fmaxf(hi.z, e.z));
     };
     fold(2, 1, mn, mx); fold(0, 1, mn, mx); fold(1, 2, mn, mx); fold(1, 0, mn, mx);
     float3 mn2 = mn, mx2 = mx;
     fold(2, 2, mn2, mx2); fold(0, 2, mn2, mx2); fold(2, 0, mn2, mx2); fold(0, 0, mn2, mx2);
-    auto half_mix = [](float x, float y) { return __fadd_rn(0.5f * x, 0.5f * y); };   // exact halves, one rounding: == the reference's FP64 mix
+    auto half_mix = [](float a, float b) { return __fadd_rn(0.5f * a, 0.5f * b); };   // exact halves, one rounding: == the reference's FP64 mix
     mn = make_float3(half_mix(mn.x, mn2.x), half_mix(mn.y, mn2.y), half_mix(mn.z, mn2.z));
     mx = make_float3(half_mix(mx.x, mx2.x), half_mix(mx.y, mx2.y), half_mix(mx.z, mx2.z));
     aa = make_float3(fminf(fmaxf(aa.x, mn.x), mx.x), fminf(fmaxf(aa.y, mn.y), mx.y), fminf(fmaxf(aa.z, mn.z), mx.z));   // :339

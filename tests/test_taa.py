@@ -131,11 +131,19 @@ def test_oracle_taa_against_the_reference_kernel_on_fixed_point_histories():
             break
         prev = cur
     fixed = np.array_equal(cur.view(np.uint16), prev.view(np.uint16))
-    # texels whose history source reproduces itself (all of them once the whole plane is a fixed point)
+    assert fixed, "the reference kernel did not reach a fixed point in 200 launches"
     again = oracle_taa(img, cur, "f16")
     u = half_ulp_diff(again, cur)
+    absd = np.abs(again.astype(np.float64) - cur.astype(np.float64))
     frac_exact = float((u == 0).mean())
-    assert fixed, f"the reference kernel did not reach a fixed point in 200 launches (oracle agrees on {frac_exact:.4f})"
-    # libm powf vs CUDA powf, FMA contraction in the compiled reference: a few texels may differ by one fp16 ulp
-    assert u.max() <= 2 and frac_exact >= 0.98, f"max {u.max()} ulps, exact fraction {frac_exact}"
+    # pixels beyond 2 ulps: the resolve's discontinuity (a decoded component within rounding of 0 turns the pixel black,
+    # src/Filter.cuh:348-351).  The compiled reference contracts its dot products into FMAs and uses CUDA's powf, so it can
+    # land on the other side of it than the un-contracted restatement; such pixels must be rare and must be exactly those
+    # where one of the two outputs is black.
+    far = (u > 2) & (absd > 1e-4)
+    far_px = far.any(axis=-1)
+    black = (again[..., :3] == 0).all(axis=-1) | (cur[..., :3] == 0).all(axis=-1)
     r.close()
+    assert frac_exact >= 0.98, f"exact fraction {frac_exact}"
+    assert far_px.mean() <= 2e-3, f"{int(far_px.sum())} of {far_px.size} pixels differ by more than 2 ulps"
+    assert (far_px & ~black).sum() == 0, f"{int((far_px & ~black).sum())} pixels differ by more than 2 ulps without either side being blacked out"
