@@ -185,6 +185,21 @@ def all_ranks(x, world):
     return [float(v) for v in t.tolist()]
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner on stdout at communicator creation when NCCL_DEBUG is VERSION or WARN; this line must
+    stay the only thing bench.py writes there.  Redirects file descriptor 1 (C-level writes included) for the block."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 class FrameRing:
     """R pre-generated frames of the pan sequence resident in HBM (procedural generator, CUDA)."""
 
@@ -379,7 +394,8 @@ def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames):
         synth.frame_device(full_g, full_c, 0, seed=0)
         live = (full_g.motion[..., 2] != 0).float().mean(dim=1).cpu().numpy()
         bounds = balanced_bounds(live + args.band_bg_cost * (1.0 - live), world, min_rows=32)
-    bd = BandDriver(W, H, rank, world, dev, storage=args.storage, levels=args.levels, bounds=bounds)
+    with stdout_to_stderr():
+        bd = BandDriver(W, H, rank, world, dev, storage=args.storage, levels=args.levels, bounds=bounds)
     sl = bd.local_rows()
     R = Wm + K
     ring_g = [GBuffer(W, bd.Height, dev) for _ in range(R)]

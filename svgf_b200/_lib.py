@@ -88,8 +88,14 @@ ABI = [
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 ]
 
+class SvgfBandStep(C.Structure):
+    """struct svgf_band_step (include/svgf_band.h)."""
+    _fields_ = [("kind", C.c_int32), ("level", C.c_int32), ("yblock0", C.c_int32), ("nyblocks", C.c_int32), ("rows", C.c_int32)]
+
+
 # include/svgf_band.h
 ABI += [
+    ("svgf_band_plan", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(SvgfBandStep), C.c_int]),
     ("svgf_band_unique_id", C.c_int, [C.c_void_p]),
     ("svgf_band_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                    C.POINTER(C.c_int32)]),

@@ -128,6 +128,51 @@ svgf_status exchange(svgf_band *b, const Plane *planes, int n_planes, int rows) 
 
 extern "C" {
 
+// The a-trous levels 1..levels-1 of one band's frame as a list of steps (level 0 always covers the whole local image).
+//  * a level below 3 recomputes its halo: it produces the band plus the rows the not-exchanging levels above it still
+//    need (8 rows around the band for level 1 when level 2 follows), rounded out to whole row blocks of 12 * 2^level rows;
+//  * a level >= 3 waits for its halo (2 * 2^level rows of the previous level's output from each neighbour);
+//  * a level whose successor is >= 3 runs the row blocks holding the rows its neighbours need FIRST, then the exchange
+//    of those rows is posted, then the interior row blocks run.
+int svgf_band_plan(int rank, int world, int band_lo, int band_hi, int local_rows, int levels, svgf_band_step *steps, int max_steps) {
+    if (levels < 2 || levels > 5 || world < 1 || rank < 0 || rank >= world || band_lo < 0 || band_hi <= band_lo || band_hi > local_rows || !steps)
+        return -1;
+    const int first_exchanged = 3;
+    int n = 0;
+    auto push = [&](int kind, int level, int yb0, int nyb, int rows) {
+        if (n < max_steps) steps[n] = svgf_band_step{kind, level, yb0, nyb, rows};
+        n++;
+    };
+    for (int l = 1; l < levels; l++) {
+        const int B = 12 << l;                     // rows per row block of this level's tile grid
+        int reach = 0;
+        for (int j = l + 1; j < levels && j < first_exchanged; j++) reach += 2 << j;
+        const int r0 = band_lo - reach > 0 ? band_lo - reach : 0, r1 = band_hi + reach < local_rows ? band_hi + reach : local_rows;
+        const int ybA = r0 / B, ybB = (r1 + B - 1) / B;
+        const bool feeds_exchange = (l + 1 < levels) && (l + 1 >= first_exchanged) && world > 1;
+        if (l >= first_exchanged && world > 1) push(SVGF_BAND_STEP_WAIT_HALO, l, 0, 0, 2 << l);
+        if (!feeds_exchange) {
+            push(SVGF_BAND_STEP_LAUNCH, l, ybA, ybB - ybA, 0);
+            continue;
+        }
+        const int halo = 2 << (l + 1);
+        int t1 = rank > 0 ? (band_lo + halo + B - 1) / B : ybA;              // top boundary blocks [ybA, t1)
+        int b0 = rank + 1 < world ? (band_hi - halo) / B : ybB;              // bottom boundary blocks [b0, ybB)
+        if (t1 > ybB) t1 = ybB;
+        if (b0 < ybA) b0 = ybA;
+        if (t1 >= b0) {                            // short band: the boundary blocks meet, nothing is left to overlap with
+            push(SVGF_BAND_STEP_LAUNCH, l, ybA, ybB - ybA, 0);
+            push(SVGF_BAND_STEP_EXCHANGE, l, 0, 0, halo);
+        } else {
+            if (t1 > ybA) push(SVGF_BAND_STEP_LAUNCH, l, ybA, t1 - ybA, 0);
+            if (ybB > b0) push(SVGF_BAND_STEP_LAUNCH, l, b0, ybB - b0, 0);
+            push(SVGF_BAND_STEP_EXCHANGE, l, 0, 0, halo);
+            push(SVGF_BAND_STEP_LAUNCH, l, t1, b0 - t1, 0);
+        }
+    }
+    return n <= max_steps ? n : -1;
+}
+
 svgf_status svgf_band_unique_id(void *id_out) {
     if (!id_out) return SVGF_INVALID_ARG;
     if (!nccl().ok) return SVGF_UNSUPPORTED;
@@ -169,7 +214,13 @@ svgf_status svgf_band_create(svgf_band **out, int device, int rank, int world, i
     int prev = -1;
     cudaGetDevice(&prev);
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        // highest priority: the level kernels fill every SM (two CTAs take all of its shared memory), so the exchange's
+        // CTAs only get in as tiles retire - and must then be picked ahead of the thousands of tiles still queued
+        int lowest = 0, greatest = 0;
+        e = cudaDeviceGetStreamPriorityRange(&lowest, &greatest);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, greatest);
+    }
     cudaEvent_t *evs[] = {&b->ev_l0, &b->ev_boundary[0], &b->ev_boundary[1], &b->ev_halo[0], &b->ev_halo[1], &b->ev_state};
     for (cudaEvent_t *ev : evs)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
@@ -265,51 +316,32 @@ svgf_status svgf_band_frame(svgf_band *b, const svgf_params *params, const svgf_
         b->state_pending = true;
     }
 
-    const int lo = b->band_lo(), hi = b->band_hi(), Hl = b->local_rows();
-    const int first_exchanged = 3;                 // levels >= 3 get their halo from the neighbours; 0..2 recompute theirs
-    int src = 0;                                   // lattice colour set holding the input of the next level
-    int n_halo = 0;
-    for (int l = 1; l < N; l++) {
-        const int S = 1 << l, B = 12 * S;          // rows per row block of this level's tile grid
-        const bool last = (l == N - 1);
-        // rows this level must produce: the band, plus what the not-exchanging levels above it still need around it
-        int reach = 0;
-        for (int j = l + 1; j < N && j < first_exchanged; j++) reach += 2 << j;
-        const int r0 = lo - reach > 0 ? lo - reach : 0, r1 = hi + reach < Hl ? hi + reach : Hl;
-        const int ybA = r0 / B, ybB = (r1 + B - 1) / B;
-        const bool feeds_exchange = !last && (l + 1 >= first_exchanged);
-        void *out = last ? bufs->filter[0] : nullptr;
-        const int kind = last ? 2 : 1;
-        if (l >= first_exchanged) BAND_TRY(band_cuda(b, cudaStreamWaitEvent(s, b->ev_halo[(l - first_exchanged) & 1], 0)));
-        if (!feeds_exchange) {
-            BAND_TRY(svgf::staged_level(c, params, slot, l, kind, nullptr, src, out, nullptr, ybA, ybB - ybA, false, s));
-        } else {
-            // boundary first: the row blocks holding the `halo` band rows next to each neighbour, then the exchange is
-            // posted, then the interior
-            const int halo = 2 << (l + 1);
-            int t1 = b->rank > 0 ? (lo + halo + B - 1) / B : ybA;                  // top boundary blocks [ybA, t1)
-            int b0 = b->rank + 1 < b->world ? (hi - halo) / B : ybB;               // bottom boundary blocks [b0, ybB)
-            if (t1 > ybB) t1 = ybB;
-            if (b0 < ybA) b0 = ybA;
-            if (t1 >= b0) {                        // short band: boundary blocks meet, nothing left to overlap with
-                BAND_TRY(svgf::staged_level(c, params, slot, l, kind, nullptr, src, out, nullptr, ybA, ybB - ybA, false, s));
-                t1 = b0 = ybB;
-            } else {
-                if (t1 > ybA) BAND_TRY(svgf::staged_level(c, params, slot, l, kind, nullptr, src, out, nullptr, ybA, t1 - ybA, false, s));
-                if (ybB > b0) BAND_TRY(svgf::staged_level(c, params, slot, l, kind, nullptr, src, out, nullptr, b0, ybB - b0, false, s));
-            }
-            cudaEvent_t evb = b->ev_boundary[n_halo & 1], evh = b->ev_halo[(l + 1 - first_exchanged) & 1];
+    // levels 1..N-1 as planned by svgf_band_plan (the same function the CPU tests check)
+    svgf_band_step steps[32];
+    const int n_steps = svgf_band_plan(b->rank, b->world, b->band_lo(), b->band_hi(), b->local_rows(), N, steps, 32);
+    if (n_steps < 0) return SVGF_UNSUPPORTED;
+    int src = 0;                                   // lattice colour set holding the input of the current level
+    int cur_level = 1, n_halo = 0;
+    for (int i = 0; i < n_steps; i++) {
+        const svgf_band_step &st = steps[i];
+        if (st.level != cur_level) { src = 1 - src; cur_level = st.level; }
+        const bool last = (st.level == N - 1);
+        if (st.kind == SVGF_BAND_STEP_WAIT_HALO) {
+            BAND_TRY(band_cuda(b, cudaStreamWaitEvent(s, b->ev_halo[(st.level - 3) & 1], 0)));
+        } else if (st.kind == SVGF_BAND_STEP_LAUNCH) {
+            BAND_TRY(svgf::staged_level(c, params, slot, st.level, last ? 2 : 1, nullptr, src, last ? bufs->filter[0] : nullptr, nullptr,
+                                        st.yblock0, st.nyblocks, false, s));
+        } else {   // SVGF_BAND_STEP_EXCHANGE: rows of THIS level's output, for level + 1
+            cudaEvent_t evb = b->ev_boundary[n_halo & 1], evh = b->ev_halo[(st.level + 1 - 3) & 1];
             BAND_TRY(band_cuda(b, cudaEventRecord(evb, s)));
             BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, evb, 0)));
-            const svgf::LatticeColour &dst = c->lat.sc[1 - src];                   // this level's output planes
+            const svgf::LatticeColour &dst = c->lat.sc[1 - src];
             const size_t row_bytes = (size_t)c->lat.pitch_pairs * 16, pad = (size_t)svgf::kLatPadY * row_bytes;
             const Plane pl[3] = {{(char *)dst.c0 + pad, row_bytes}, {(char *)dst.c1 + pad, row_bytes}, {(char *)dst.lz + pad, row_bytes}};
-            BAND_TRY(exchange(b, pl, 3, halo));
+            BAND_TRY(exchange(b, pl, 3, st.rows));
             BAND_TRY(band_cuda(b, cudaEventRecord(evh, b->side)));
             n_halo++;
-            if (b0 > t1) BAND_TRY(svgf::staged_level(c, params, slot, l, kind, nullptr, src, out, nullptr, t1, b0 - t1, false, s));
         }
-        src = 1 - src;
     }
     return SVGF_OK;
 }

@@ -27,6 +27,70 @@ def test_band_create_validates_its_partition_before_touching_a_device():
     assert not h.value
 
 
+def _plan(rank, world, lo, hi, rows, levels):
+    steps = (_lib.SvgfBandStep * 32)()
+    n = _lib.lib().svgf_band_plan(rank, world, lo, hi, rows, levels, steps, 32)
+    assert n >= 0
+    return [(s.kind, s.level, s.yblock0, s.nyblocks, s.rows) for s in steps[:n]]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("levels", [2, 3, 4, 5])
+@pytest.mark.parametrize("height", [1080, 4320, 333])
+def test_band_plan_covers_what_each_level_must_produce(world, levels, height):
+    """svgf_band_plan is the schedule svgf_band_frame executes.  For every rank: each level's launches are disjoint row-block
+    ranges whose union covers the band plus the rows the non-exchanging levels above it need; a level that feeds an
+    exchange has produced the rows its neighbours need BEFORE the exchange is posted; levels >= 3 wait for their halo."""
+    LAUNCH, EXCHANGE, WAIT = 0, 1, 2
+    base = height // world
+    if world > 1 and base < 32:
+        pytest.skip("bands shorter than the apron")
+    for rank in range(world):
+        y0 = rank * base
+        y1 = height if rank == world - 1 else y0 + base
+        ly0, ly1 = (max(0, y0 - 32), min(height, y1 + 32)) if world > 1 else (y0, y1)
+        lo, hi, rows = y0 - ly0, y1 - ly0, ly1 - ly0
+        plan = _plan(rank, world, lo, hi, rows, levels)
+        assert [lv for _, lv, *_ in plan] == sorted(lv for _, lv, *_ in plan), "levels out of order"
+        for l in range(1, levels):
+            B = 12 << l
+            reach = sum(2 << j for j in range(l + 1, min(levels, 3)))
+            need = set(range(max(0, lo - reach), min(rows, hi + reach)))
+            mine = [s for s in plan if s[1] == l]
+            covered, before_exchange = set(), set()
+            seen_exchange = False
+            for kind, _, yb0, nyb, r in mine:
+                if kind == LAUNCH:
+                    blk = set(range(yb0 * B, (yb0 + nyb) * B))
+                    assert not (blk & covered), f"rank {rank} level {l}: row blocks launched twice"
+                    covered |= blk
+                    if not seen_exchange:
+                        before_exchange |= blk
+                elif kind == EXCHANGE:
+                    seen_exchange = True
+                    assert r == 2 << (l + 1)
+                    halo = set()
+                    if rank > 0:
+                        halo |= set(range(lo, lo + r))
+                    if rank + 1 < world:
+                        halo |= set(range(hi - r, hi))
+                    assert halo <= before_exchange, f"rank {rank} level {l}: exchange posted before its rows were produced"
+            assert need <= covered, f"rank {rank} level {l}: rows {sorted(need - covered)[:4]}... never produced"
+            assert seen_exchange == (world > 1 and l + 1 < levels and l + 1 >= 3)
+            assert (mine[0][0] == WAIT) == (world > 1 and l >= 3)
+            if mine[0][0] == WAIT:
+                assert mine[0][4] == 2 << l
+
+
+def test_band_plan_rejects_what_the_driver_does_not_do():
+    steps = (_lib.SvgfBandStep * 32)()
+    lib = _lib.lib()
+    assert lib.svgf_band_plan(0, 2, 0, 500, 532, 6, steps, 32) == -1      # more than 5 levels
+    assert lib.svgf_band_plan(0, 2, 0, 500, 532, 1, steps, 32) == -1      # a single level has no staged run
+    assert lib.svgf_band_plan(2, 2, 0, 500, 532, 5, steps, 32) == -1
+    assert lib.svgf_band_plan(0, 2, 0, 500, 532, 5, steps, 2) == -1       # list too short
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("size,levels,storage", [((1920, 1080), 5, "f16"), ((1030, 420), 5, "f32"), ((1280, 720), 4, "f16"),
                                                  ((1280, 720), 3, "f16"), ((1280, 720), 2, "f16")])
