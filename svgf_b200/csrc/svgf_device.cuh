@@ -83,6 +83,16 @@ struct Guide {
     unsigned short *mid;
     float4 *seg;
 };
+// Row groups of 64 x 3 outputs per CTA of the lattice kernel: 4 -> 256 threads, tiles of 12 rows, two CTAs per SM;
+// 2 -> 128 threads, tiles of 6 rows, four CTAs per SM (tools/build_exp.sh 2).  A launch's row-block unit stays 12 * STEP rows.
+#ifndef SVGF_EXP
+#define SVGF_EXP 0      // build-time experiment selector (tools/build_exp.sh); 0 = the shipped form
+#endif
+#if SVGF_EXP == 2
+constexpr int kLatRowGroups = 2;
+#else
+constexpr int kLatRowGroups = 4;
+#endif
 // Padding (pixels / rows) around the context-owned lattice planes of svgf_kernels_lattice.cuh: the widest halo, 2 * 2^4.
 constexpr int kLatPadX = 32, kLatPadY = 32;
 

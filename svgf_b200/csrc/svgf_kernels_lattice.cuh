@@ -30,14 +30,13 @@
 #include "svgf_device.cuh"
 #include "svgf_kernels_packed.cuh"
 
-#ifndef SVGF_EXP
-#define SVGF_EXP 0      // build-time experiment selector (tools/build_exp.sh); 0 = the shipped form
-#endif
-
 namespace svgf {
 
 template <int STEP> struct LatGeom {
-    static constexpr int tile_rows = kPkRows * kPkRowGroups;   // 12 output rows
+    static constexpr int tile_rows = kPkRows * kLatRowGroups;  // 12 output rows (6 with two row groups)
+    static constexpr int block_rows = kPkRows * kPkRowGroups;  // 12: lattice rows of a launch's row block (what the band driver counts in)
+    static constexpr int subtiles = block_rows / tile_rows;    // tiles stacked in a row block
+    static constexpr int threads = kPkPairs * kLatRowGroups;
     static constexpr int rows = tile_rows + 4;                 // 16 staged rows
     static constexpr int pairs = kPkPairs + 2 * STEP;          // 64 + halo of 2*STEP pixels = STEP pairs on each side
     static constexpr int npairs = pairs * rows;
@@ -45,7 +44,7 @@ template <int STEP> struct LatGeom {
     static constexpr uint32_t off_c0 = 0, off_c1 = plane16, off_lz = 2 * plane16, off_n0 = 3 * plane16, off_n1 = 4 * plane16;
     static constexpr uint32_t off_misc = 4 * plane16 + plane8;   // two mbarriers + the uniform-tile reduction records
     static constexpr size_t smem_bytes = (size_t)off_misc + 256 + 128;   // + slack to align the base to 128 bytes
-    static_assert(plane16 % 128 == 0 && plane8 % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(plane16 % 128 == 0 && plane8 % 16 == 0, "TMA destinations (multiples of plane16) must stay 128-byte aligned");
 };
 
 struct LatticeArgs {
@@ -167,7 +166,7 @@ constexpr float kSegWild = 0.0f, kSegUniform = 1.0f, kSegMixed = 2.0f;
 // LAST: the level's result is the caller's plane in the storage format (`out`); otherwise it is the next lattice
 // level's input (`dst`).
 template <bool F32, int STEP, int TERMS, bool LAST>
-__global__ void __launch_bounds__(kPkThreads, 2)
+__global__ void __launch_bounds__(kPkPairs * kLatRowGroups, 8 / kLatRowGroups)
 atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_constant__ CUtensorMap mC1,
                       const __grid_constant__ CUtensorMap mLZ, const __grid_constant__ CUtensorMap mN0,
                       const __grid_constant__ CUtensorMap mN1, LatticeArgs a, const float *__restrict__ guide_dz,
@@ -206,11 +205,12 @@ atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_cons
 
     // ---- uniform-normal test over the 6 x 16 segments that cover the staged tile (guide data: not written by the
     //      previous level; it runs while the colour planes are already in flight) ----
-    float4 sg = make_float4(0.f, 0.f, 0.f, kSegWild);
-    if (tid < 96) {
+    constexpr int kSegEntries = G::rows * 6, kSegWarps = (kSegEntries + 31) / 32;
+    if (tid < kSegWarps * 32) {                // whole warps: the lanes past the last entry carry a wildcard
+        float4 sg = make_float4(0.f, 0.f, 0.f, kSegWild);
         const int r = tid / 6, sx = (x0 >> 5) - 1 + (tid - r * 6);
         const int gy = y0 + (r - 2) * STEP;
-        if (sx >= 0 && sx < a.segs_x && gy >= 0 && gy < a.H) sg = __ldg(seg + (size_t)gy * a.segs_x + sx);
+        if (tid < kSegEntries && sx >= 0 && sx < a.segs_x && gy >= 0 && gy < a.H) sg = __ldg(seg + (size_t)gy * a.segs_x + sx);
         const unsigned has = __ballot_sync(0xffffffffu, sg.w == kSegUniform);
         const int leader = has ? (__ffs(has) - 1) : 0;
         const float rx = __shfl_sync(0xffffffffu, sg.x, leader), ry = __shfl_sync(0xffffffffu, sg.y, leader),
@@ -237,7 +237,7 @@ atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_cons
     {
         bool have = false;
 #pragma unroll
-        for (int w = 0; w < 3; w++) {
+        for (int w = 0; w < kSegWarps; w++) {
             const float4 r = sRed[w];
             if (r.w == kSegMixed) uniform_n = false;
             else if (r.w == kSegUniform) {

@@ -38,14 +38,14 @@ lattice_clear_kernel(LatticeColour a, LatticeColour b, LatticeNormals n, size_t 
 }
 
 // One plane at one dilation: the padded plane [rows][pitch_pairs] of `elems_per_pair` 8-byte elements viewed as
-// {pitch_pairs * elems_per_pair, step, rows / step}; box = 16 rows of one phase x the tile's pairs.
+// {pitch_pairs * elems_per_pair, step, rows / step}; box = the tile's staged rows (16) of one phase x the tile's pairs.
 bool encode_plane(CUtensorMap *map, void *base, int pitch_pairs, int rows, int elems_per_pair, int step) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return false;
     const cuuint64_t row_elems = (cuuint64_t)pitch_pairs * elems_per_pair;
     const cuuint64_t dims[3] = {row_elems, (cuuint64_t)step, (cuuint64_t)(rows / step)};
     const cuuint64_t strides[2] = {row_elems * 8, row_elems * 8 * (cuuint64_t)step};   // bytes, dims 1 and 2
-    const cuuint32_t box[3] = {(cuuint32_t)((kTileW / 2 + 2 * step) * elems_per_pair), 1u, 16u};
+    const cuuint32_t box[3] = {(cuuint32_t)((kTileW / 2 + 2 * step) * elems_per_pair), 1u, (cuuint32_t)(3 * kLatRowGroups + 4)};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;

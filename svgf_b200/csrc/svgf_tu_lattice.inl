@@ -24,9 +24,9 @@ svgf_status launch_lattice(svgf_ctx *c, const AtrousTiledArgs &t, int guide_slot
     const CUtensorMap *m = L.map[t.level];
     const int q = src * 3;
     cudaLaunchConfig_t cfg = {};
-    const int all_yblocks = (c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP);
-    cfg.gridDim = dim3((c->W + kTileW - 1) / kTileW, (t.nyblocks > 0 ? t.nyblocks : all_yblocks) * STEP);
-    cfg.blockDim = dim3(kPkThreads);
+    const int all_yblocks = (c->H + G::block_rows * STEP - 1) / (G::block_rows * STEP);
+    cfg.gridDim = dim3((c->W + kTileW - 1) / kTileW, (t.nyblocks > 0 ? t.nyblocks : all_yblocks) * G::subtiles * STEP);
+    cfg.blockDim = dim3(G::threads);
     cfg.dynamicSmemBytes = G::smem_bytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
