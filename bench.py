@@ -576,7 +576,6 @@ def run_ours(args, rank, world, local):
         gseq.f.close()
 
     # ---- end to end through the host-buffer entry point: pinned host inputs, H2D + frame + D2H per step ----
-    from svgf_b200 import synth
     n_host = 4
     cdt = torch.float16 if args.storage == "f16" else torch.float32
     host = []
@@ -589,13 +588,13 @@ def run_ours(args, rank, world, local):
         host.append(hp)
     result = torch.empty(H, W, 4, dtype=cdt).pin_memory()
     torch.cuda.synchronize()
-    Ke = max(4, min(K, args.e2e_steps))
+    Ke = max(4, min(K, args.e2e_steps)) if args.e2e_steps > 0 else 0      # --e2e-steps 0: profiling runs only
 
     def e2e_step(t, reset=False):
         hp = host[t % n_host]
         f.frame_host(hp["normal"], hp["uv"], hp["motion"], hp["colour"], result=result, reset=reset)
 
-    for t in range(3):
+    for t in range(3 if Ke else 0):
         e2e_step(t, reset=(t == 0))
     barrier(world)
     e0.record(stream)
@@ -603,9 +602,9 @@ def run_ours(args, rank, world, local):
         e2e_step(t)
     e1.record(stream)
     barrier(world)
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1), world)
+    e2e_ms = max(max_over_ranks(e0.elapsed_time(e1), world), 1e-9)
     e2e_value = world * W * H * Ke / (e2e_ms * 1e-3) / 1e9
-    checksum = float(result.float().sum())       # the host-side read of the step's result
+    checksum = float(result.float().sum()) if Ke else None      # the host-side read of the step's result
     h2d, d2h = IN_BYTES_PER_PX[args.storage] * W * H, OUT_BYTES_PER_PX[args.storage] * W * H
     ceiling = None
     if not args.skip_extras:
@@ -647,10 +646,10 @@ def run_ours(args, rank, world, local):
         "dtype": "f32 compute, %s storage" % ("fp16" if args.storage == "f16" else "fp32"), "data": "synthetic",
         "config": cfg,
         "e2e": {"value": round(e2e_value, 4), "unit": "Gpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": round(e2e_ms / Ke, 4), "steps": Ke,
+                "ms_per_step": round(e2e_ms / max(1, Ke), 4), "steps": Ke,
                 "api": "svgf_frame_host (pinned host buffers; copy-in, kernels and copy-out of consecutive frames overlap on three streams; timed region starts with the pipeline drained)",
                 "result_checksum": checksum, "pcie_ceiling": ceiling,
-                "frac_of_pcie_ceiling": round(ceiling["ms_per_step_at_ceiling"] / (e2e_ms / Ke), 4) if ceiling else None},
+                "frac_of_pcie_ceiling": round(ceiling["ms_per_step_at_ceiling"] / (e2e_ms / Ke), 4) if (ceiling and Ke) else None},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "a-trous levels (%d launches/frame)" % at_launches,
                      "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",

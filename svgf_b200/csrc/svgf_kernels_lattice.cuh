@@ -183,7 +183,6 @@ atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_cons
     float4 *sN0 = reinterpret_cast<float4 *>(smem + G::off_n0);
     float2 *sN1 = reinterpret_cast<float2 *>(smem + G::off_n1);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + G::off_misc);          // [0] colour planes, [1] normal planes
-    float4 *sRed = reinterpret_cast<float4 *>(smem + G::off_misc + 64);        // 3 warp records of the segment test
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * kTileW;
@@ -203,24 +202,27 @@ atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_cons
         tma_load_3d(sLZ, &mLZ, cx, phase, cy, &bar[0]);
     }
 
-    // ---- uniform-normal test over the 6 x 16 segments that cover the staged tile (guide data: not written by the
-    //      previous level; it runs while the colour planes are already in flight) ----
-    constexpr int kSegEntries = G::rows * 6, kSegWarps = (kSegEntries + 31) / 32;
-    if (tid < kSegWarps * 32) {                // whole warps: the lanes past the last entry carry a wildcard
+    // ---- uniform-normal test, PER WARP: a warp filters 64 x 3 outputs and taps (64 + 4 STEP) x 7 texels, which 4 x 7 of
+    //      the guide's 32-pixel row segments cover - one map entry per lane (guide data: not written by the previous level;
+    //      the loads run while the colour planes are already in flight).  A warp whose segments agree on one normal takes
+    //      the uniform form whatever the rest of the tile looks like; the normal planes are loaded iff some warp needs them.
+    const int pcx = tid & (kPkPairs - 1), tg = tid / kPkPairs;
+    bool uniform_n;
+    float3 nref;
+    {
+        const int lane = tid & 31, half = (tid >> 5) & 1;              // which 64-pixel half of the tile row this warp owns
+        const int r = lane >> 2, sx = (x0 >> 5) + 2 * half - 1 + (lane & 3);
+        const int gy = y0 + (tg * kPkRows + r - 2) * STEP;
         float4 sg = make_float4(0.f, 0.f, 0.f, kSegWild);
-        const int r = tid / 6, sx = (x0 >> 5) - 1 + (tid - r * 6);
-        const int gy = y0 + (r - 2) * STEP;
-        if (tid < kSegEntries && sx >= 0 && sx < a.segs_x && gy >= 0 && gy < a.H) sg = __ldg(seg + (size_t)gy * a.segs_x + sx);
+        if (r < kPkRows + 4 && sx >= 0 && sx < a.segs_x && gy >= 0 && gy < a.H) sg = __ldg(seg + (size_t)gy * a.segs_x + sx);
         const unsigned has = __ballot_sync(0xffffffffu, sg.w == kSegUniform);
         const int leader = has ? (__ffs(has) - 1) : 0;
-        const float rx = __shfl_sync(0xffffffffu, sg.x, leader), ry = __shfl_sync(0xffffffffu, sg.y, leader),
-                    rz = __shfl_sync(0xffffffffu, sg.z, leader);
-        const bool ok = sg.w == kSegWild || (sg.w == kSegUniform && sg.x == rx && sg.y == ry && sg.z == rz);
-        const bool all_ok = __all_sync(0xffffffffu, ok);
-        if ((tid & 31) == 0) sRed[tid >> 5] = make_float4(rx, ry, rz, !all_ok ? kSegMixed : (has ? kSegUniform : kSegWild));
+        nref = make_float3(__shfl_sync(0xffffffffu, sg.x, leader), __shfl_sync(0xffffffffu, sg.y, leader), __shfl_sync(0xffffffffu, sg.z, leader));
+        const bool ok = sg.w == kSegWild || (sg.w == kSegUniform && sg.x == nref.x && sg.y == nref.y && sg.z == nref.z);
+        uniform_n = __all_sync(0xffffffffu, ok) && a.uniform_tiles != 0;
+        if (!has) nref = make_float3(0.f, 0.f, 0.f);                    // nothing but background: no tap carries weight
     }
     // depth derivatives of this thread's outputs (guide data as well)
-    const int pcx = tid & (kPkPairs - 1), tg = tid / kPkPairs;
     const int gx = x0 + 2 * pcx;
     const int pcol = pcx + STEP;
     const int row0 = tg * kPkRows + 2;
@@ -230,24 +232,8 @@ atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_cons
         const int gy = y0 + (tg * kPkRows + j) * STEP;
         dz[j] = (gx < a.W && gy < a.H) ? __ldg(reinterpret_cast<const float2 *>(guide_dz + (size_t)gy * a.W + gx)) : make_float2(0.f, 0.f);
     }
-    __syncthreads();   // barrier init + the segment records
-
-    bool uniform_n = a.uniform_tiles != 0;
-    float3 nref = make_float3(0.f, 0.f, 0.f);
-    {
-        bool have = false;
-#pragma unroll
-        for (int w = 0; w < kSegWarps; w++) {
-            const float4 r = sRed[w];
-            if (r.w == kSegMixed) uniform_n = false;
-            else if (r.w == kSegUniform) {
-                if (!have) { nref = make_float3(r.x, r.y, r.z); have = true; }
-                else if (r.x != nref.x || r.y != nref.y || r.z != nref.z) uniform_n = false;
-            }
-        }
-    }
-
-    if (!uniform_n && tid == 0) {
+    const bool tile_needs_normals = __syncthreads_or(!uniform_n) != 0;   // also publishes the barrier init
+    if (tile_needs_normals && tid == 0) {
         mbar_expect_tx(&bar[1], G::plane16 + G::plane8);
         tma_load_3d(sN0, &mN0, cx, phase, cy, &bar[1]);
         tma_load_3d(sN1, &mN1, cx >> 1, phase, cy, &bar[1]);

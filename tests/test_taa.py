@@ -136,14 +136,17 @@ def test_oracle_taa_against_the_reference_kernel_on_fixed_point_histories():
     u = half_ulp_diff(again, cur)
     absd = np.abs(again.astype(np.float64) - cur.astype(np.float64))
     frac_exact = float((u == 0).mean())
-    # pixels beyond 2 ulps: the resolve's discontinuity (a decoded component within rounding of 0 turns the pixel black,
-    # src/Filter.cuh:348-351).  The compiled reference contracts its dot products into FMAs and uses CUDA's powf, so it can
-    # land on the other side of it than the un-contracted restatement; such pixels must be rare and must be exactly those
-    # where one of the two outputs is black.
+    # values beyond 2 ulps: the resolve is ill-conditioned where a decoded component is within rounding of 0 (the PAL-YUV
+    # matrices are inverses only to ~5e-6): pow(x, 0.5) turns a 1e-8 difference there into 1e-4, on the negative side into
+    # NaN and a blacked-out pixel (src/Filter.cuh:348-351).  The compiled reference contracts its dot products into FMAs and
+    # uses CUDA's powf, so such values may differ from the un-contracted restatement; they must be rare, and every one of
+    # them must be such a near-zero channel (dark on one side) or a blacked-out pixel.
     far = (u > 2) & (absd > 1e-4)
-    far_px = far.any(axis=-1)
     black = (again[..., :3] == 0).all(axis=-1) | (cur[..., :3] == 0).all(axis=-1)
+    dark = np.minimum(again.astype(np.float32), cur.astype(np.float32)) < 0.03
     r.close()
     assert frac_exact >= 0.98, f"exact fraction {frac_exact}"
-    assert far_px.mean() <= 2e-3, f"{int(far_px.sum())} of {far_px.size} pixels differ by more than 2 ulps"
-    assert (far_px & ~black).sum() == 0, f"{int((far_px & ~black).sum())} pixels differ by more than 2 ulps without either side being blacked out"
+    assert far.any(axis=-1).mean() <= 2e-3, f"{int(far.any(axis=-1).sum())} of {far.shape[0] * far.shape[1]} pixels differ by more than 2 ulps"
+    unexplained = far & ~dark & ~black[..., None]
+    assert unexplained.sum() == 0, f"{int(unexplained.sum())} values differ by more than 2 ulps away from the discontinuity: " \
+                                   f"{again[unexplained][:4]} vs {cur[unexplained][:4]}"
