@@ -42,7 +42,11 @@ template <int STEP> struct LatGeom {
     static constexpr int npairs = pairs * rows;
     static constexpr uint32_t plane16 = (uint32_t)npairs * 16u, plane8 = (uint32_t)npairs * 8u;
     static constexpr uint32_t off_c0 = 0, off_c1 = plane16, off_lz = 2 * plane16, off_n0 = 3 * plane16, off_n1 = 4 * plane16;
+#if SVGF_EXP == 3
+    static constexpr uint32_t off_misc = 3 * plane16;            // TIMING PROBE (tools/build_exp.sh 3): no room for the normal planes, every tile forced uniform, 3 CTAs/SM
+#else
     static constexpr uint32_t off_misc = 4 * plane16 + plane8;   // two mbarriers + the uniform-tile reduction records
+#endif
     static constexpr size_t smem_bytes = (size_t)off_misc + 256 + 128;   // + slack to align the base to 128 bytes
     static_assert(plane16 % 128 == 0 && plane8 % 16 == 0, "TMA destinations (multiples of plane16) must stay 128-byte aligned");
 };
@@ -166,7 +170,11 @@ constexpr float kSegWild = 0.0f, kSegUniform = 1.0f, kSegMixed = 2.0f;
 // LAST: the level's result is the caller's plane in the storage format (`out`); otherwise it is the next lattice
 // level's input (`dst`).
 template <bool F32, int STEP, int TERMS, bool LAST>
+#if SVGF_EXP == 3
+__global__ void __launch_bounds__(kPkPairs * kLatRowGroups, 3)
+#else
 __global__ void __launch_bounds__(kPkPairs * kLatRowGroups, 8 / kLatRowGroups)
+#endif
 atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_constant__ CUtensorMap mC1,
                       const __grid_constant__ CUtensorMap mLZ, const __grid_constant__ CUtensorMap mN0,
                       const __grid_constant__ CUtensorMap mN1, LatticeArgs a, const float *__restrict__ guide_dz,
@@ -220,6 +228,9 @@ atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_cons
         nref = make_float3(__shfl_sync(0xffffffffu, sg.x, leader), __shfl_sync(0xffffffffu, sg.y, leader), __shfl_sync(0xffffffffu, sg.z, leader));
         const bool ok = sg.w == kSegWild || (sg.w == kSegUniform && sg.x == nref.x && sg.y == nref.y && sg.z == nref.z);
         uniform_n = __all_sync(0xffffffffu, ok) && a.uniform_tiles != 0;
+#if SVGF_EXP == 3 || SVGF_EXP == 4
+        uniform_n = true;       // TIMING PROBES ONLY: wrong pixels on mixed tiles
+#endif
         if (!has) nref = make_float3(0.f, 0.f, 0.f);                    // nothing but background: no tap carries weight
     }
     // depth derivatives of this thread's outputs (guide data as well)
