@@ -202,7 +202,6 @@ svgf_status launch_atrous_fused01(svgf_ctx *c, const svgf_params *p, int guide_s
     t.uniform_tiles = (p->flags & SVGF_FLAG_NO_UNIFORM_TILES) ? 0 : 1;
     t.var_blur = nullptr;
     t.yblock0 = 0; t.nyblocks = 0;
-    t.seg = nullptr; t.segs_x = 0;
     t.kL_scale = kLog2e / p->phi_colour;
     t.kZ_scale = kLog2e / p->phi_depth;        // level 0; the kernel halves it for level 1
     t.k1 = a.nt.k1; t.k2 = a.nt.k2; t.k3 = a.nt.k3; t.k4 = a.nt.k4; t.k5 = a.nt.k5;
@@ -223,7 +222,6 @@ int tiled_args(const svgf_ctx *c, const svgf_params *p, int level, const float *
     t->uniform_tiles = (p->flags & SVGF_FLAG_NO_UNIFORM_TILES) ? 0 : 1;
     t->var_blur = var_blur;
     t->yblock0 = 0; t->nyblocks = 0;
-    t->seg = nullptr; t->segs_x = 0;     // set by the packed launchers from the guide slot
     t->kL_scale = kLog2e / p->phi_colour;
     t->kZ_scale = kLog2e / ((float)(1 << level) * p->phi_depth);
     t->k1 = nt.k1; t->k2 = nt.k2; t->k3 = nt.k3; t->k4 = nt.k4; t->k5 = nt.k5;

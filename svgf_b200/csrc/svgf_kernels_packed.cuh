@@ -245,7 +245,6 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     using G = PackedGeom<STEP>;
     constexpr int kThreads = kPkPairs * (G::tile_rows / R);   // R = 3: 256 threads, R = 4: 192
     static_assert(G::tile_rows % R == 0, "row groups must tile the 12 rows");
-    static_assert(R + 4 <= 8, "the per-warp segment test holds one row of 4 segments per 4 lanes");
     static_assert(!(HC && F32), "half-precision colour tiles are exact for fp16 storage only");
     using CT = typename ColourPlane<F32>::texel;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -261,12 +260,13 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     const int y0 = yblock * (G::tile_rows * STEP) + phase;
 
     // ---- stage the tile, one pixel pair per thread and iteration; all global loads first ----
-    // Uniform-normal shortcut, decided PER WARP from the guide's segment map (one float4 per 32-pixel row segment: all
-    // background / one normal / mixed): a warp filters 64 x R outputs and taps (64 + 4 STEP) x (R + 4) texels, covered by
-    // 4 x (R + 4) segments - one entry per lane.  When they agree on one normal - any planar surface: floors, walls, box
-    // faces; background texels are wildcards, their weight is 0 through z = 1e30 - the normal weight of all the warp's
-    // (centre, tap) pairs is one number and the taps run the UNIF form (12 instead of 19 packed operations, no normal
-    // loads).  The exponent is formed by the same single FMA either way, so no output bit depends on the decision.
+    // Uniform-normal tiles: when every in-image texel the tile stages (halo included) carries the same non-zero
+    // normal as the tile's first pixel - any planar surface: floors, walls, box faces - the normal weight of all
+    // 24 x 1536 (centre, tap) pairs is one number, and the taps run the UNIF form (12 instead of 19 packed
+    // operations, no normal loads).  Compared as floats: equal values give equal dot products (+0 == -0 included),
+    // NaN never matches.  Texels outside the image are excluded: their weight is 0 through z = +inf either way.
+    const float4 nref = __ldg(guide_n + (size_t)min(y0, a.H - 1) * a.W + x0);
+    bool same_n = a.uniform_tiles && (nref.y != 0.0f || nref.z != 0.0f || nref.w != 0.0f);
     constexpr int kIters = (G::npairs + kThreads - 1) / kThreads;
     CT rc0[kIters], rc1[kIters];
     float4 rg0[kIters], rg1[kIters];
@@ -289,6 +289,8 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
             }
             rg0[i] = __ldg(guide_n + gi);
             rg1[i] = __ldg(guide_n + gi + 1);
+            same_n &= (rg0[i].y == nref.y) & (rg0[i].z == nref.z) & (rg0[i].w == nref.w) & (rg1[i].y == nref.y) & (rg1[i].z == nref.z) &
+                      (rg1[i].w == nref.w);
         }
     }
 #pragma unroll
@@ -309,27 +311,7 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
             sL[idx] = make_float2(luminance(r0, g0, b0), luminance(r1, g1, b1));
         }
     }
-    __syncthreads();
-    bool uniform_n;
-    float un = 0.f, pn = 0.f;
-    {
-        float4 sg = make_float4(0.f, 0.f, 0.f, 0.f);    // this lane's segment-map entry
-        {
-            const int lane = tid & 31, half = (tid >> 5) & 1, wtg = tid / kPkPairs;
-            const int r = lane >> 2, sx = (x0 >> 5) + 2 * half - 1 + (lane & 3);
-            const int gy = y0 + (wtg * R + r - 2) * STEP;
-            if (a.seg && r < R + 4 && sx >= 0 && sx < a.segs_x && gy >= 0 && gy < a.H) sg = __ldg(a.seg + (size_t)gy * a.segs_x + sx);
-        }
-        const unsigned has = __ballot_sync(0xffffffffu, sg.w == 1.0f);
-        const int leader = has ? (__ffs(has) - 1) : 0;
-        const float rx = __shfl_sync(0xffffffffu, sg.x, leader), ry = __shfl_sync(0xffffffffu, sg.y, leader), rz = __shfl_sync(0xffffffffu, sg.z, leader);
-        const bool ok = sg.w == 0.0f || (sg.w == 1.0f && sg.x == rx && sg.y == ry && sg.z == rz);
-        uniform_n = __all_sync(0xffffffffu, ok) && a.uniform_tiles != 0 && a.seg != nullptr;
-        PkCoef kk;
-        kk.k1 = a.k1; kk.k2 = a.k2; kk.k3 = a.k3; kk.k4 = a.k4; kk.k5 = a.k5;
-        if (has) pk_normal_term<TERMS>(rx, ry, rz, rx, ry, rz, kk, un, pn);
-        else pk_normal_term<TERMS>(0.f, 0.f, 0.f, 0.f, 0.f, 0.f, kk, un, pn);     // nothing but background: no tap carries weight
-    }
+    const bool uniform_n = __syncthreads_and(same_n) != 0;
 
     const int pcx = tid & (kPkPairs - 1), tg = tid / kPkPairs;
     const int gx = x0 + 2 * pcx;
@@ -337,6 +319,8 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
     const int row0 = tg * R + 2;
     PkCoef k;
     k.k1 = a.k1; k.k2 = a.k2; k.k3 = a.k3; k.k4 = a.k4; k.k5 = a.k5;
+    float un, pn;
+    pk_normal_term<TERMS>(nref.y, nref.z, nref.w, nref.y, nref.z, nref.w, k, un, pn);
 
     PkCentre C[R];
     PkAcc A[R];

@@ -49,8 +49,6 @@ struct AtrousTiledArgs {
     int tiles_x, tiles_y;       // tiles_y counts (row block, phase) pairs
     int uniform_tiles;          // packed kernel: allow the uniform-normal tile shortcut
     const float *var_blur;      // packed kernel: blurred variance plane (SVGF_VARIANCE_PREFILTER_GAUSS3) or nullptr
-    const float4 *seg;          // packed kernel: the guide's segment map (svgf_device.cuh) and its row pitch in entries
-    int segs_x;
     int yblock0, nyblocks;      // packed / lattice kernels: restrict the launch to row blocks [yblock0, yblock0 + nyblocks) of the
                                 // level's tile grid (a row block = 12 * STEP image rows, all STEP phases); nyblocks == 0: all
 };

@@ -12,8 +12,6 @@ svgf_status launch_staged(svgf_ctx *c, AtrousTiledArgs a, int guide_slot, const 
     auto kern = atrous_packed_kernel<F32, STEP, TERMS, kPkRows, false, false, true>;
     static std::atomic<unsigned long long> configured{0};
     SVGF_CUDA(c, configure_smem_once(configured, c->device, kern, G::smem_bytes));
-    a.seg = c->guide[guide_slot].seg;
-    a.segs_x = (c->W + 31) / 32;
     const int all_yblocks = (c->H + G::tile_rows * STEP - 1) / (G::tile_rows * STEP);
     const dim3 grid((c->W + kTileW - 1) / kTileW, (a.nyblocks > 0 ? a.nyblocks : all_yblocks) * STEP);
     kern<<<grid, kPkThreads, G::smem_bytes, s>>>(a, c->guide[guide_slot].n, c->guide[guide_slot].dz, (const CT *)in, (CT *)nullptr,
