@@ -58,8 +58,25 @@ taa_kernel(int W, int H, const typename ColourPlane<F32>::texel *__restrict__ fi
            const typename ColourPlane<F32>::texel *__restrict__ history, typename ColourPlane<F32>::texel *__restrict__ out) {
     __shared__ float4 sYuv[kTaaTW * kTaaTH];    // y u v (w unused)
     __shared__ float4 sSq[kTaaTW * kTaaTH];     // r^2 g^2 b^2 (w unused)
+    __shared__ int sXs[3][kTaaBW], sYs[3][kTaaBH];   // floor texel of uv - 1/size, uv, uv + 1/size per column / row of the block
     const int bx0 = blockIdx.x * kTaaBW, by0 = blockIdx.y * kTaaBH;
     const int tx0 = max(bx0 - 3, 0), ty0 = max(by0 - 3, 0);      // window origin: floor texels reach x - 2 (one more for rounding slack)
+    const float inv_w = 1.0f / (float)W, inv_h = 1.0f / (float)H;
+    // the sampling positions depend on the column (row) only: evaluated once per block, in the reference's float expressions
+    bool covered = true;
+    if (threadIdx.x < 3 * kTaaBW) {
+        const int o = threadIdx.x / kTaaBW, cxx = threadIdx.x - o * kTaaBW;
+        const float u = (float)(bx0 + cxx) * inv_w;                                  // :296
+        const int t = taa_texel(o == 0 ? u - inv_w : o == 1 ? u : u + inv_w, W);
+        sXs[o][cxx] = t;
+        covered = t >= tx0 && t < tx0 + kTaaTW;
+    } else if (threadIdx.x < 3 * kTaaBW + 3 * kTaaBH) {
+        const int k = threadIdx.x - 3 * kTaaBW, o = k / kTaaBH, cyy = k - o * kTaaBH;
+        const float v = (float)(by0 + cyy) * inv_h;
+        const int t = taa_texel(o == 0 ? v - inv_h : o == 1 ? v : v + inv_h, H);
+        sYs[o][cyy] = t;
+        covered = t >= ty0 && t < ty0 + kTaaTH;
+    }
     for (int i = threadIdx.x; i < kTaaTW * kTaaTH; i += kTaaBW * kTaaBH) {
         const int ty = i / kTaaTW, tx = i - ty * kTaaTW;
         const int gx = min(tx0 + tx, W - 1), gy = min(ty0 + ty, H - 1);
@@ -69,19 +86,20 @@ taa_kernel(int W, int H, const typename ColourPlane<F32>::texel *__restrict__ fi
         sYuv[i] = make_float4(taa_dot3(r, g, b, 0.299f, 0.587f, 0.114f), taa_dot3(r, g, b, -0.14713f, -0.28886f, 0.436f),
                               taa_dot3(r, g, b, 0.615f, -0.51499f, -0.10001f), 0.f);
     }
-    __syncthreads();
-    const int x = bx0 + (threadIdx.x & (kTaaBW - 1)), y = by0 + threadIdx.x / kTaaBW;
+    // every tap of the block inside the window?  (it is, by the arithmetic above; the test makes the window an optimisation
+    // instead of an assumption: a block that fails it takes its taps from global memory)
+    const bool window_ok = __syncthreads_and(covered) != 0;
+    const int cxl = threadIdx.x & (kTaaBW - 1), cyl = threadIdx.x / kTaaBW;
+    const int x = bx0 + cxl, y = by0 + cyl;
     if (x >= W || y >= H) return;
-    const float inv_w = 1.0f / (float)W, inv_h = 1.0f / (float)H;
-    const float u = (float)x * inv_w, v = (float)y * inv_h;                          // :296
-    const int xs[3] = {taa_texel(u - inv_w, W), taa_texel(u, W), taa_texel(u + inv_w, W)};
-    const int ys[3] = {taa_texel(v - inv_h, H), taa_texel(v, H), taa_texel(v + inv_h, H)};
+    const int xs[3] = {sXs[0][cxl], sXs[1][cxl], sXs[2][cxl]};
+    const int ys[3] = {sYs[0][cyl], sYs[1][cyl], sYs[2][cyl]};
     // encoded texel (ix, iy) of the neighbourhood, and optionally its squared rgb
     auto tap = [&](int ix, int iy, float4 *sq) -> float4 {
-        const int lx = xs[ix] - tx0, ly = ys[iy] - ty0;
-        if (lx >= 0 && lx < kTaaTW && ly >= 0 && ly < kTaaTH) {
-            if (sq) *sq = sSq[ly * kTaaTW + lx];
-            return sYuv[ly * kTaaTW + lx];
+        if (window_ok) {
+            const int li = (ys[iy] - ty0) * kTaaTW + (xs[ix] - tx0);
+            if (sq) *sq = sSq[li];
+            return sYuv[li];
         }
         const float4 c = clamp01(ColourPlane<F32>::decode(__ldg(filtered + (size_t)ys[iy] * W + xs[ix])));
         const float r = __fmul_rn(c.x, c.x), g = __fmul_rn(c.y, c.y), b = __fmul_rn(c.z, c.z);
