@@ -448,6 +448,7 @@ def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames):
     # ---- timing: a fresh sequence, inputs consumed in place from the resident ring ----
     stream = torch.cuda.current_stream(dev)
     bd.Reset()
+    bd.params.flags = args.flags          # e.g. 512 = SVGF_FLAG_BAND_NO_EXCHANGE (diagnostics: compute only)
     keep = bd.RenderBuffer
 
     def step(t):

@@ -114,6 +114,10 @@ typedef enum svgf_depth_test_mode { SVGF_DEPTH_TEST_ABSOLUTE = 0, SVGF_DEPTH_TES
  * previous level's tail). */
 #define SVGF_FLAG_NO_DEPENDENT_LAUNCH 256u
 
+/* svgf_band_frame only, DIAGNOSTICS: skip every neighbour exchange (pixels near the band edges come out wrong).  Shows what a
+ * band's frame costs without communication and cross-rank waiting. */
+#define SVGF_FLAG_BAND_NO_EXCHANGE 512u
+
 /* Kernel family that ran an a-trous level (svgf_last_dispatch). */
 typedef enum svgf_dispatch_family {
     SVGF_FAMILY_NONE = 0,

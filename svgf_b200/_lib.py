@@ -15,6 +15,7 @@ SVGF_DEPTH_TEST_ABSOLUTE, SVGF_DEPTH_TEST_RELATIVE = 0, 1
 SVGF_FLAG_NO_GUIDE_CACHE, SVGF_FLAG_NO_LEVEL_FUSION, SVGF_FLAG_BASIC_KERNELS, SVGF_FLAG_NO_UNIFORM_TILES = 1, 2, 4, 8
 SVGF_FLAG_FUSE_LEVELS_01 = 16
 SVGF_FLAG_NO_STAGED_LEVELS, SVGF_FLAG_ATROUS_BULK, SVGF_FLAG_ATROUS_STREAM, SVGF_FLAG_NO_DEPENDENT_LAUNCH = 32, 64, 128, 256
+SVGF_FLAG_BAND_NO_EXCHANGE = 512
 # svgf_dispatch_family (svgf_last_dispatch)
 SVGF_FAMILY_BASIC, SVGF_FAMILY_PACKED, SVGF_FAMILY_PACKED_STAGED, SVGF_FAMILY_LATTICE = 1, 2, 3, 4
 SVGF_FAMILY_BULK, SVGF_FAMILY_STREAM, SVGF_FAMILY_FUSED01 = 5, 6, 7

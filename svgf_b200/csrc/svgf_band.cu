@@ -78,6 +78,7 @@ struct svgf_band {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_l0 = nullptr, ev_boundary[2] = {nullptr, nullptr}, ev_halo[2] = {nullptr, nullptr}, ev_state = nullptr;
     bool state_pending = false;
+    bool dry_run = false;          // SVGF_FLAG_BAND_NO_EXCHANGE of the current call
     int last_err = 0;
 
     int band_lo() const { return y0 - ly0; }     // local row of the first owned row
@@ -106,6 +107,7 @@ svgf_status band_nccl(svgf_band *b, int r) {
 // Refresh `rows` apron rows on each side of the band, for every plane, with the neighbours' band rows: ONE grouped
 // send/recv on the side stream.
 svgf_status exchange(svgf_band *b, const Plane *planes, int n_planes, int rows) {
+    if (b->dry_run) return SVGF_OK;
     const NcclApi &n = nccl();
     const int lo = b->band_lo(), hi = b->band_hi();
     BAND_TRY(band_nccl(b, n.GroupStart()));
@@ -285,6 +287,7 @@ svgf_status svgf_band_frame(svgf_band *b, const svgf_params *params, const svgf_
     if (N < 2 || N > 5) return SVGF_UNSUPPORTED;
     if (bufs->ping_pong != 0 && bufs->ping_pong != 1) return SVGF_INVALID_ARG;
     const int P = bufs->ping_pong;
+    b->dry_run = (params->flags & SVGF_FLAG_BAND_NO_EXCHANGE) != 0;
     int prev_dev = -1;
     cudaGetDevice(&prev_dev);
     if (prev_dev != b->device) BAND_TRY(band_cuda(b, cudaSetDevice(b->device)));

@@ -71,6 +71,8 @@ def test_lattice_level_against_the_oracle_teacher_forced(size, storage, level, s
     start = f.FilterBuffer[0].clone()
     # level - 1 alone (packed kernel, storage format out): the teacher for level `level`
     mid = _run_levels(f, level - 1, 1, _lib.SVGF_FLAG_NO_STAGED_LEVELS)
+    # the packed kernel itself at this size (ragged tiles, > 3840 wide) against the oracle, same inputs
+    assert_close(npy(mid), _oracle_level(of, npy(start), level - 1), storage, f"packed level {level - 1} {size} {scene}")
     want = _oracle_level(of, npy(mid), level)
     # the same two levels as one staged run
     f.FilterBuffer[0].copy_(start)
