@@ -394,8 +394,51 @@ def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames):
         synth.frame_device(full_g, full_c, 0, seed=0)
         live = (full_g.motion[..., 2] != 0).float().mean(dim=1).cpu().numpy()
         bounds = balanced_bounds(live + args.band_bg_cost * (1.0 - live), world, min_rows=32)
-    with stdout_to_stderr():
-        bd = BandDriver(W, H, rank, world, dev, storage=args.storage, levels=args.levels, bounds=bounds)
+    def make_driver(bnds):
+        with stdout_to_stderr():
+            return BandDriver(W, H, rank, world, dev, storage=args.storage, levels=args.levels, bounds=bnds)
+
+    calibration = []
+    if args.band_balance >= 2 and world > 1:
+        # measured balance: a few frames WITHOUT exchanges (SVGF_FLAG_BAND_NO_EXCHANGE: every rank runs at its own speed)
+        # give each band's cost per row; the boundaries are moved to equalise the predicted times.  Twice.
+        for it in range(2):
+            cal = make_driver(bounds)
+            cal.Reset()
+            cal.params.flags = 512
+            sl_c = cal.local_rows()
+            g_c = GBuffer(W, cal.Height, dev)
+            c_c = torch.empty(cal.Height, W, 4, dtype=cdt, device=dev)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            cur = torch.cuda.current_stream(dev)
+            for t in range(7):
+                synth.frame_device(full_g, full_c, t, seed=0)
+                g_c.normal.copy_(full_g.normal[sl_c]); g_c.uv.copy_(full_g.uv[sl_c]); g_c.motion.copy_(full_g.motion[sl_c])
+                c_c.copy_(full_c[sl_c])
+                P = cal.PingPongInx
+                cal.Framebuffer[P].normal.copy_(g_c.normal); cal.Framebuffer[P].uv.copy_(g_c.uv); cal.Framebuffer[P].motion.copy_(g_c.motion)
+                cal.RenderBuffer[P].copy_(c_c)
+                if t == 4:
+                    ev0.record(cur)
+                cal.Filter()
+                cal.EndFrame()
+            ev1.record(cur)
+            torch.cuda.synchronize()
+            t_rank = all_ranks(ev0.elapsed_time(ev1) / 3, world)
+            rows_rank = all_ranks(float(cal.y1 - cal.y0), world)
+            cal.close()
+            del cal, g_c, c_c
+            calibration.append([round(v, 4) for v in t_rank])
+            speed = [r / max(t, 1e-6) for r, t in zip(rows_rank, t_rank)]             # band rows per ms
+            # time to equalise: sum_i rows_i' = H with rows_i' / speed_i equal  =>  rows_i' = H * speed_i / sum(speed)
+            share = [v / sum(speed) for v in speed]
+            new_rows = [max(32, int(round(H * v))) for v in share]
+            new_rows[-1] += H - sum(new_rows)
+            bounds = [0]
+            for r in new_rows:
+                bounds.append(bounds[-1] + r)
+            barrier(world)
+    bd = make_driver(bounds)
     sl = bd.local_rows()
     R = Wm + K
     ring_g = [GBuffer(W, bd.Height, dev) for _ in range(R)]
@@ -484,7 +527,8 @@ def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames):
     return {"workload": f"BASELINE configs[3]: {W}x{H} frames in {world} horizontal band(s), native band driver (include/svgf_band.h): "
                         "NCCL send/recv of 16 + 32 halo rows before levels 3 and 4, boundary row blocks first, state exchange under levels 1-4",
             "value": round(value, 4), "unit": "Gpix/s", "ms_per_step": round(ms_max / K, 5), "steps": K, "warmup": Wm, "scaling": "strong",
-            "band_bounds": bounds, "local_rows_by_rank": rows, "ms_per_step_by_rank": [round(v, 4) for v in ms_by_rank],
+            "band_bounds": bounds, "band_balance": {0: "equal heights", 1: "background share of the first frame", 2: "measured: two calibration passes without exchanges"}[min(args.band_balance, 2)],
+            "calibration_ms_by_rank": calibration or None, "local_rows_by_rank": rows, "ms_per_step_by_rank": [round(v, 4) for v in ms_by_rank],
             "gpu_launches": int(launches),
             "bit_identical_to_one_gpu": (bad_total == 0) if check_frames else None, "checked_frames": check_frames, "mismatching_bytes": bad_total,
             "frac_of_n_gpu_hbm_peak": round(frame_bytes / (ms_max / K * 1e-3) / 1e9 / (peak * world), 4)}
@@ -682,7 +726,7 @@ def run_bands(args, rank, world, local):
         return None
     cfg = base_config(W, H, args.levels, args.storage)
     cfg["workload"] = rec.pop("workload")
-    for k in ("band_bounds", "local_rows_by_rank", "ms_per_step_by_rank", "bit_identical_to_one_gpu", "checked_frames", "mismatching_bytes"):
+    for k in ("band_bounds", "band_balance", "calibration_ms_by_rank", "local_rows_by_rank", "ms_per_step_by_rank", "bit_identical_to_one_gpu", "checked_frames", "mismatching_bytes"):
         cfg[k] = rec.pop(k)
     return {"metric": "svgf_frame_throughput", "value": rec["value"], "unit": "Gpix/s", "n_gpus": world, "steps": rec["steps"], "warmup": rec["warmup"],
             "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -860,7 +904,7 @@ def main():
     ap.add_argument("--prefilter", type=int, default=0, help="svgf_params.variance_prefilter (1 = 3x3 Gaussian, not in the reference)")
     ap.add_argument("--reproj", type=int, default=0, help="svgf_params.reproj_mode (1 = bilinear 2x2, not in the reference)")
     ap.add_argument("--flags", type=int, default=0, help="svgf_params.flags for A/B runs (8 = no uniform-normal tile shortcut, 32 = no staged levels)")
-    ap.add_argument("--band-balance", type=int, default=1, help="bands: 1 = band heights balanced by estimated work (background rows are cheap), 0 = equal heights")
+    ap.add_argument("--band-balance", type=int, default=2, help="bands: 0 = equal heights, 1 = heights balanced by the background share of the first frame, 2 = 1 + two measured calibration passes")
     ap.add_argument("--band-bg-cost", type=float, default=0.45, help="bands: cost of a background pixel relative to a filtered one")
     ap.add_argument("--mode", default="streams", choices=["streams", "bands"],
                     help="multi-GPU sharding: independent frame streams per GPU (weak scaling, default) or one frame in "

@@ -63,12 +63,13 @@ svgf_status svgf_band_sync(svgf_band *b, void *stream);
  * executes exactly this list).  band_lo / band_hi: local rows of the owned band [band_lo, band_hi) inside a local image of
  * local_rows rows.  Steps, in issue order:
  *   LAUNCH     level `level` over row blocks [yblock0, yblock0 + nyblocks) of its tile grid (a block = 12 * 2^level rows)
+ *              and, when nyblocks1 > 0, [yblock1, yblock1 + nyblocks1) in the same launch (the two boundary strips)
  *   EXCHANGE   post the exchange of `rows` band rows of level `level`'s output with each neighbour (for level + 1)
  *   WAIT_HALO  level `level` is about to start: wait for the exchange of its `rows`-row halo
  * Returns the number of steps (<= max_steps), or -1 for unsupported arguments. */
 enum { SVGF_BAND_STEP_LAUNCH = 0, SVGF_BAND_STEP_EXCHANGE = 1, SVGF_BAND_STEP_WAIT_HALO = 2 };
 typedef struct svgf_band_step {
-    int32_t kind, level, yblock0, nyblocks, rows;
+    int32_t kind, level, yblock0, nyblocks, rows, yblock1, nyblocks1;
 } svgf_band_step;
 int svgf_band_plan(int rank, int world, int band_lo, int band_hi, int local_rows, int levels, svgf_band_step *steps, int max_steps);
 

@@ -91,7 +91,8 @@ ABI = [
 
 class SvgfBandStep(C.Structure):
     """struct svgf_band_step (include/svgf_band.h)."""
-    _fields_ = [("kind", C.c_int32), ("level", C.c_int32), ("yblock0", C.c_int32), ("nyblocks", C.c_int32), ("rows", C.c_int32)]
+    _fields_ = [("kind", C.c_int32), ("level", C.c_int32), ("yblock0", C.c_int32), ("nyblocks", C.c_int32), ("rows", C.c_int32),
+                ("yblock1", C.c_int32), ("nyblocks1", C.c_int32)]
 
 
 # include/svgf_band.h

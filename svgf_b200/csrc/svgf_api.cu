@@ -201,7 +201,7 @@ svgf_status launch_atrous_fused01(svgf_ctx *c, const svgf_params *p, int guide_s
     t.W = c->W; t.H = c->H; t.level = 0; t.tiles_x = t.tiles_y = 0;
     t.uniform_tiles = (p->flags & SVGF_FLAG_NO_UNIFORM_TILES) ? 0 : 1;
     t.var_blur = nullptr;
-    t.yblock0 = 0; t.nyblocks = 0;
+    t.yblock0 = 0; t.nyblocks = 0; t.yblock1 = 0; t.nyblocks1 = 0;
     t.kL_scale = kLog2e / p->phi_colour;
     t.kZ_scale = kLog2e / p->phi_depth;        // level 0; the kernel halves it for level 1
     t.k1 = a.nt.k1; t.k2 = a.nt.k2; t.k3 = a.nt.k3; t.k4 = a.nt.k4; t.k5 = a.nt.k5;
@@ -221,7 +221,7 @@ int tiled_args(const svgf_ctx *c, const svgf_params *p, int level, const float *
     t->W = c->W; t->H = c->H; t->level = level; t->tiles_x = t->tiles_y = 0;
     t->uniform_tiles = (p->flags & SVGF_FLAG_NO_UNIFORM_TILES) ? 0 : 1;
     t->var_blur = var_blur;
-    t->yblock0 = 0; t->nyblocks = 0;
+    t->yblock0 = 0; t->nyblocks = 0; t->yblock1 = 0; t->nyblocks1 = 0;
     t->kL_scale = kLog2e / p->phi_colour;
     t->kZ_scale = kLog2e / ((float)(1 << level) * p->phi_depth);
     t->k1 = nt.k1; t->k2 = nt.k2; t->k3 = nt.k3; t->k4 = nt.k4; t->k5 = nt.k5;
@@ -386,16 +386,16 @@ void prof_mark(svgf_ctx *c, int k, cudaStream_t s) {
 }  // namespace
 
 namespace svgf {
-// One level of a staged run restricted to row blocks [yb0, yb0 + nyb) of the level's tile grid (nyb == 0: the whole image);
+// One level of a staged run restricted to row blocks [yb0, yb0 + nyb) (+ [yb1, yb1 + nyb1)) of the level's tile grid (nyb == 0: the whole image);
 // used by the band driver (svgf_band.cu), which runs the boundary rows of a level first.  kind 0: first level - packed
 // kernel, storage-format `in` -> lattice planes sc[idx];  kind 1: lattice sc[idx] -> sc[1 - idx];  kind 2: lattice sc[idx]
 // -> storage-format `out`.
 svgf_status staged_level(svgf_ctx *c, const svgf_params *p, int guide_slot, int level, int kind, const void *in, int idx, void *out,
-                         void *hist_colour, int yb0, int nyb, bool pdl, cudaStream_t s) {
+                         void *hist_colour, int yb0, int nyb, int yb1, int nyb1, bool pdl, cudaStream_t s) {
     const bool f32 = c->storage == SVGF_STORE_F32;
     AtrousTiledArgs t;
     const int terms = tiled_args(c, p, level, nullptr, &t);
-    t.yblock0 = yb0; t.nyblocks = nyb;
+    t.yblock0 = yb0; t.nyblocks = nyb; t.yblock1 = yb1; t.nyblocks1 = nyb1;     // the second range is honoured by the lattice kernel only
     if (kind == 0) {
         note_dispatch(c, level, kFamPackedStaged);
         return f32 ? atrous_packed_staged_f32(c, terms, t, guide_slot, in, idx, level == 0 ? hist_colour : nullptr, s)

@@ -1,14 +1,13 @@
 // svgf_band.cu — include/svgf_band.h: one frame in horizontal bands, one band per GPU, halos exchanged with NCCL send/recv.
 //
 // What runs where, per frame (N = 5 levels; main = the caller's stream, side = the driver's exchange stream):
-//   main: [wait state exchange of frame t-1]  temporal + variance (whole local image)  level 0 (whole local image)
-//   side:                                                                              [after level 0] exchange STATE(t) ----.
-//   main: level 1 (band +- 8 rows)   level 2: boundary row blocks -> [ev]   level 2: interior row blocks                    |
-//   side:                                                              `-> exchange 16 rows of level 2's output -> [ev]     |
-//   main:                       [wait]  level 3: boundary row blocks -> [ev]   level 3: interior row blocks                 |
-//   side:                                                                `-> exchange 32 rows of level 3's output -> [ev]   |
-//   main:                                                      [wait]  level 4 (band rows) -> filter[0]                     |
-//   frame t+1, main: [wait] <------------------------------------------------------------------------------------------------'
+//   main: [wait STATE(t-1)]  temporal + variance (whole local image)  level 0 (whole local image)
+//   main: level 1 (band +- 8 rows)   level 2: both boundary strips -> [ev]   level 2: interior row blocks
+//   side:                                                               `-> exchange 16 rows of level 2's output -> [ev]
+//   main:                       [wait]  level 3: both boundary strips -> [ev]   level 3: interior row blocks
+//   side:                                                                 `-> exchange 32 rows of level 3's output + STATE(t) -> [ev]
+//   main:                                                      [wait]  level 4 (band rows) -> filter[0]
+//   frame t+1, main: [wait STATE(t)]
 // Levels 0..2 do not exchange: their halos (2 + 4 + 8 rows), the variance pass's 7x7 window and the motion vectors' reach are
 // covered by computing those stages up to 17 + max_motion rows into the 32-row apron.  Only lattice planes travel for
 // the per-level exchanges (the level that follows reads them by TMA); whole padded rows, so one contiguous block per plane.
@@ -104,25 +103,28 @@ svgf_status band_nccl(svgf_band *b, int r) {
         if (st_ != SVGF_OK) return st_;   \
     } while (0)
 
-// Refresh `rows` apron rows on each side of the band, for every plane, with the neighbours' band rows: ONE grouped
-// send/recv on the side stream.
-svgf_status exchange(svgf_band *b, const Plane *planes, int n_planes, int rows) {
+// Refresh the apron rows on each side of the band with the neighbours' band rows, for every plane of up to two plane sets
+// (each with its own row count): ONE grouped send/recv on the side stream.
+struct PlaneSet { const Plane *planes; int n; int rows; };
+svgf_status exchange(svgf_band *b, const PlaneSet *sets, int n_sets) {
     if (b->dry_run) return SVGF_OK;
     const NcclApi &n = nccl();
     const int lo = b->band_lo(), hi = b->band_hi();
     BAND_TRY(band_nccl(b, n.GroupStart()));
-    for (int k = 0; k < n_planes; k++) {
-        const Plane &p = planes[k];
-        const size_t bytes = (size_t)rows * p.row_bytes;
-        if (b->rank > 0) {                    // my top band rows -> upper neighbour's bottom apron; its bottom band rows -> my top apron
-            BAND_TRY(band_nccl(b, n.Send(p.base + (size_t)lo * p.row_bytes, bytes, kNcclUint8, b->rank - 1, b->comm, b->side)));
-            BAND_TRY(band_nccl(b, n.Recv(p.base + (size_t)(lo - rows) * p.row_bytes, bytes, kNcclUint8, b->rank - 1, b->comm, b->side)));
+    for (int q = 0; q < n_sets; q++)
+        for (int k = 0; k < sets[q].n; k++) {
+            const Plane &p = sets[q].planes[k];
+            const int rows = sets[q].rows;
+            const size_t bytes = (size_t)rows * p.row_bytes;
+            if (b->rank > 0) {                // my top band rows -> upper neighbour's bottom apron; its bottom band rows -> my top apron
+                BAND_TRY(band_nccl(b, n.Send(p.base + (size_t)lo * p.row_bytes, bytes, kNcclUint8, b->rank - 1, b->comm, b->side)));
+                BAND_TRY(band_nccl(b, n.Recv(p.base + (size_t)(lo - rows) * p.row_bytes, bytes, kNcclUint8, b->rank - 1, b->comm, b->side)));
+            }
+            if (b->rank + 1 < b->world) {
+                BAND_TRY(band_nccl(b, n.Send(p.base + (size_t)(hi - rows) * p.row_bytes, bytes, kNcclUint8, b->rank + 1, b->comm, b->side)));
+                BAND_TRY(band_nccl(b, n.Recv(p.base + (size_t)hi * p.row_bytes, bytes, kNcclUint8, b->rank + 1, b->comm, b->side)));
+            }
         }
-        if (b->rank + 1 < b->world) {
-            BAND_TRY(band_nccl(b, n.Send(p.base + (size_t)(hi - rows) * p.row_bytes, bytes, kNcclUint8, b->rank + 1, b->comm, b->side)));
-            BAND_TRY(band_nccl(b, n.Recv(p.base + (size_t)hi * p.row_bytes, bytes, kNcclUint8, b->rank + 1, b->comm, b->side)));
-        }
-    }
     return band_nccl(b, n.GroupEnd());
 }
 
@@ -141,8 +143,8 @@ int svgf_band_plan(int rank, int world, int band_lo, int band_hi, int local_rows
         return -1;
     const int first_exchanged = 3;
     int n = 0;
-    auto push = [&](int kind, int level, int yb0, int nyb, int rows) {
-        if (n < max_steps) steps[n] = svgf_band_step{kind, level, yb0, nyb, rows};
+    auto push = [&](int kind, int level, int yb0, int nyb, int rows, int yb1 = 0, int nyb1 = 0) {
+        if (n < max_steps) steps[n] = svgf_band_step{kind, level, yb0, nyb, rows, yb1, nyb1};
         n++;
     };
     for (int l = 1; l < levels; l++) {
@@ -166,8 +168,10 @@ int svgf_band_plan(int rank, int world, int band_lo, int band_hi, int local_rows
             push(SVGF_BAND_STEP_LAUNCH, l, ybA, ybB - ybA, 0);
             push(SVGF_BAND_STEP_EXCHANGE, l, 0, 0, halo);
         } else {
-            if (t1 > ybA) push(SVGF_BAND_STEP_LAUNCH, l, ybA, t1 - ybA, 0);
-            if (ybB > b0) push(SVGF_BAND_STEP_LAUNCH, l, b0, ybB - b0, 0);
+            // both boundary strips in ONE launch (two row-block ranges): a strip alone is one or two waves of tiles
+            if (t1 > ybA && ybB > b0) push(SVGF_BAND_STEP_LAUNCH, l, ybA, t1 - ybA, 0, b0, ybB - b0);
+            else if (t1 > ybA) push(SVGF_BAND_STEP_LAUNCH, l, ybA, t1 - ybA, 0);
+            else if (ybB > b0) push(SVGF_BAND_STEP_LAUNCH, l, b0, ybB - b0, 0);
             push(SVGF_BAND_STEP_EXCHANGE, l, 0, 0, halo);
             push(SVGF_BAND_STEP_LAUNCH, l, t1, b0 - t1, 0);
         }
@@ -307,22 +311,29 @@ svgf_status svgf_band_frame(svgf_band *b, const svgf_params *params, const svgf_
 
     // level 0 over the whole local image: it also writes the normal planes every later level reads in the apron, and the
     // colour history of the apron rows is replaced by the neighbours' below
-    BAND_TRY(svgf::staged_level(c, params, slot, 0, 0, bufs->filter[0], 0, nullptr, bufs->render[P], 0, 0, false, s));
+    BAND_TRY(svgf::staged_level(c, params, slot, 0, 0, bufs->filter[0], 0, nullptr, bufs->render[P], 0, 0, 0, 0, false, s));
+    // next frame's previous-frame state - colour history (level 0's output), moments and history lengths - is final from here
+    // on.  It travels with the LAST halo exchange of the frame (one NCCL launch fewer; it is not needed before the next
+    // frame's temporal pass), or on its own right away when no level exchanges a halo.
     BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_l0, s)));
-    {   // next frame's previous-frame state: colour history (level 0's output), moments and history lengths are final now
-        BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, b->ev_l0, 0)));
-        const size_t ct = c->storage == SVGF_STORE_F32 ? 16 : 8, mt = c->storage == SVGF_STORE_F32 ? 8 : 4;
-        const Plane st[3] = {{(char *)bufs->render[P], (size_t)b->W * ct}, {(char *)bufs->moments[P], (size_t)b->W * mt},
-                             {(char *)bufs->history, (size_t)b->W}};
-        BAND_TRY(exchange(b, st, 3, SVGF_BAND_APRON));
-        BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_state, b->side)));
-        b->state_pending = true;
-    }
+    const size_t ct = c->storage == SVGF_STORE_F32 ? 16 : 8, mt = c->storage == SVGF_STORE_F32 ? 8 : 4;
+    const Plane state[3] = {{(char *)bufs->render[P], (size_t)b->W * ct}, {(char *)bufs->moments[P], (size_t)b->W * mt},
+                            {(char *)bufs->history, (size_t)b->W}};
+    const PlaneSet state_set = {state, 3, SVGF_BAND_APRON};
 
     // levels 1..N-1 as planned by svgf_band_plan (the same function the CPU tests check)
     svgf_band_step steps[32];
     const int n_steps = svgf_band_plan(b->rank, b->world, b->band_lo(), b->band_hi(), b->local_rows(), N, steps, 32);
     if (n_steps < 0) return SVGF_UNSUPPORTED;
+    int last_exchange = -1;
+    for (int i = 0; i < n_steps; i++)
+        if (steps[i].kind == SVGF_BAND_STEP_EXCHANGE) last_exchange = i;
+    if (last_exchange < 0) {
+        BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, b->ev_l0, 0)));
+        BAND_TRY(exchange(b, &state_set, 1));
+        BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_state, b->side)));
+        b->state_pending = true;
+    }
     int src = 0;                                   // lattice colour set holding the input of the current level
     int cur_level = 1, n_halo = 0;
     for (int i = 0; i < n_steps; i++) {
@@ -333,16 +344,21 @@ svgf_status svgf_band_frame(svgf_band *b, const svgf_params *params, const svgf_
             BAND_TRY(band_cuda(b, cudaStreamWaitEvent(s, b->ev_halo[(st.level - 3) & 1], 0)));
         } else if (st.kind == SVGF_BAND_STEP_LAUNCH) {
             BAND_TRY(svgf::staged_level(c, params, slot, st.level, last ? 2 : 1, nullptr, src, last ? bufs->filter[0] : nullptr, nullptr,
-                                        st.yblock0, st.nyblocks, false, s));
+                                        st.yblock0, st.nyblocks, st.yblock1, st.nyblocks1, false, s));
         } else {   // SVGF_BAND_STEP_EXCHANGE: rows of THIS level's output, for level + 1
             cudaEvent_t evb = b->ev_boundary[n_halo & 1], evh = b->ev_halo[(st.level + 1 - 3) & 1];
             BAND_TRY(band_cuda(b, cudaEventRecord(evb, s)));
-            BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, evb, 0)));
+            BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, evb, 0)));       // (implies level 0: same stream, earlier)
             const svgf::LatticeColour &dst = c->lat.sc[1 - src];
             const size_t row_bytes = (size_t)c->lat.pitch_pairs * 16, pad = (size_t)svgf::kLatPadY * row_bytes;
             const Plane pl[3] = {{(char *)dst.c0 + pad, row_bytes}, {(char *)dst.c1 + pad, row_bytes}, {(char *)dst.lz + pad, row_bytes}};
-            BAND_TRY(exchange(b, pl, 3, st.rows));
+            const PlaneSet sets[2] = {{pl, 3, st.rows}, state_set};
+            BAND_TRY(exchange(b, sets, i == last_exchange ? 2 : 1));
             BAND_TRY(band_cuda(b, cudaEventRecord(evh, b->side)));
+            if (i == last_exchange) {
+                BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_state, b->side)));
+                b->state_pending = true;
+            }
             n_halo++;
         }
     }

@@ -114,7 +114,7 @@ svgf_status atrous_lattice_f32(svgf_ctx *c, int terms, const AtrousTiledArgs &a,
 
 // svgf_api.cu, for the band driver (svgf_band.cu)
 svgf_status staged_level(svgf_ctx *c, const svgf_params *p, int guide_slot, int level, int kind, const void *in, int idx, void *out,
-                         void *hist_colour, int yb0, int nyb, bool pdl, cudaStream_t s);
+                         void *hist_colour, int yb0, int nyb, int yb1, int nyb1, bool pdl, cudaStream_t s);
 bool staged_run_possible(const svgf_ctx *c, const svgf_params *p, const void *a, const void *b, const void *hist_colour, int first, int n);
 
 // one a-trous level (a.level = 0..4) / levels 0+1 fused; terms = series terms of the normal weight (3, 4 or 5);

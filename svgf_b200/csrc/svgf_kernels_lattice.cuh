@@ -58,7 +58,8 @@ struct LatticeArgs {
     float kL_scale, kZ_scale;   // log2e / phi_colour, log2e / (STEP * phi_depth)
     float k1, k2, k3, k4, k5;   // normal-term series coefficients
     int uniform_tiles;          // 0: never take the uniform-normal shortcut (SVGF_FLAG_NO_UNIFORM_TILES)
-    int yblock0;                // first row block of this launch (band driver: boundary rows first, svgf_band.cu)
+    int yblock0, nyblocks0, yblock1;   // row blocks of this launch: [yblock0, yblock0 + nyblocks0) then [yblock1, ...) (band driver:
+                                       // boundary rows first, svgf_band.cu); nyblocks0 == 0: one range from yblock0
 };
 
 // ---- TMA / mbarrier primitives (PTX ISA: cp.async.bulk.tensor, mbarrier) -----------------------------------------
@@ -194,11 +195,16 @@ atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_cons
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * kTileW;
-    const int yblock = blockIdx.y / STEP + a.yblock0, phase = blockIdx.y % STEP;
-    const int y0 = yblock * (G::tile_rows * STEP) + phase;
+    // blockIdx.y = ((row block, sub-tile), phase): a row block is 12 lattice rows of every phase, cut into `subtiles` tiles;
+    // the launch covers row blocks [yblock0, yblock0 + nyblocks0) and then [yblock1, ...) (one range when nyblocks0 == 0)
+    const int by = blockIdx.y / STEP, phase = blockIdx.y % STEP;
+    const int yb = by / G::subtiles, sub = by % G::subtiles;
+    const int yblock = (a.nyblocks0 == 0 || yb < a.nyblocks0) ? a.yblock0 + yb : a.yblock1 + (yb - a.nyblocks0);
+    const int lrow0 = yblock * G::block_rows + sub * G::tile_rows;  // first lattice row (of this phase) of the tile
+    const int y0 = lrow0 * STEP + phase;
 
     const int cx = x0 - 2 * STEP + kLatPadX;                       // 8-byte elements == pixels for the 16-byte-per-pair planes
-    const int cy = yblock * G::tile_rows - 2 + kLatPadY / STEP;     // row block of the first staged row (kLatPadY % STEP == 0)
+    const int cy = lrow0 - 2 + kLatPadY / STEP;                     // lattice row of the first staged row (kLatPadY % STEP == 0)
     if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);

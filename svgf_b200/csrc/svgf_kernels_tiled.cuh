@@ -51,6 +51,7 @@ struct AtrousTiledArgs {
     const float *var_blur;      // packed kernel: blurred variance plane (SVGF_VARIANCE_PREFILTER_GAUSS3) or nullptr
     int yblock0, nyblocks;      // packed / lattice kernels: restrict the launch to row blocks [yblock0, yblock0 + nyblocks) of the
                                 // level's tile grid (a row block = 12 * STEP image rows, all STEP phases); nyblocks == 0: all
+    int yblock1, nyblocks1;     // lattice kernel: a second range in the same launch (band driver: both boundary strips at once)
 };
 
 // -log2 of the reference's tap kernel KW[|xx|] * KW[|yy|], KW = {1, 2/3, 1/6} as floats (src/Filter.cuh:540,582):

@@ -20,12 +20,12 @@ svgf_status launch_lattice(svgf_ctx *c, const AtrousTiledArgs &t, int guide_slot
     a.kL_scale = t.kL_scale; a.kZ_scale = t.kZ_scale;
     a.k1 = t.k1; a.k2 = t.k2; a.k3 = t.k3; a.k4 = t.k4; a.k5 = t.k5;
     a.uniform_tiles = t.uniform_tiles;
-    a.yblock0 = t.yblock0;
+    a.yblock0 = t.yblock0; a.nyblocks0 = t.nyblocks1 > 0 ? t.nyblocks : 0; a.yblock1 = t.yblock1;
     const CUtensorMap *m = L.map[t.level];
     const int q = src * 3;
     cudaLaunchConfig_t cfg = {};
     const int all_yblocks = (c->H + G::block_rows * STEP - 1) / (G::block_rows * STEP);
-    cfg.gridDim = dim3((c->W + kTileW - 1) / kTileW, (t.nyblocks > 0 ? t.nyblocks : all_yblocks) * G::subtiles * STEP);
+    cfg.gridDim = dim3((c->W + kTileW - 1) / kTileW, (t.nyblocks > 0 ? t.nyblocks + t.nyblocks1 : all_yblocks) * G::subtiles * STEP);
     cfg.blockDim = dim3(G::threads);
     cfg.dynamicSmemBytes = G::smem_bytes;
     cfg.stream = s;

@@ -31,7 +31,7 @@ def _plan(rank, world, lo, hi, rows, levels):
     steps = (_lib.SvgfBandStep * 32)()
     n = _lib.lib().svgf_band_plan(rank, world, lo, hi, rows, levels, steps, 32)
     assert n >= 0
-    return [(s.kind, s.level, s.yblock0, s.nyblocks, s.rows) for s in steps[:n]]
+    return [(s.kind, s.level, s.yblock0, s.nyblocks, s.rows, s.yblock1, s.nyblocks1) for s in steps[:n]]
 
 
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
@@ -59,9 +59,10 @@ def test_band_plan_covers_what_each_level_must_produce(world, levels, height):
             mine = [s for s in plan if s[1] == l]
             covered, before_exchange = set(), set()
             seen_exchange = False
-            for kind, _, yb0, nyb, r in mine:
+            for kind, _, yb0, nyb, r, yb1, nyb1 in mine:
                 if kind == LAUNCH:
-                    blk = set(range(yb0 * B, (yb0 + nyb) * B))
+                    blk = set(range(yb0 * B, (yb0 + nyb) * B)) | set(range(yb1 * B, (yb1 + nyb1) * B))
+                    assert len(blk) == (nyb + nyb1) * B, "the two ranges of a launch overlap"
                     assert not (blk & covered), f"rank {rank} level {l}: row blocks launched twice"
                     covered |= blk
                     if not seen_exchange:
