@@ -454,16 +454,6 @@ svgf_status svgf_create(svgf_ctx **out, int device, int width, int height, svgf_
     if (prop.major != 10) return SVGF_UNSUPPORTED;  // sm_100a only: no other code path exists in this library
     DeviceGuard guard(device);
     if (!guard.ok) return SVGF_CUDA_ERROR;
-#if SVGF_EXP == 5
-    {   // EXPERIMENT (tools/build_exp.sh 5): one shared-memory carve-out for every kernel of the frame, so that kernels of
-        // different contexts / streams can share an SM without an L1 / shared-memory reconfiguration in between
-        auto carve = [](auto kern) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); };
-        carve(temporal_kernel<false, false, false>); carve(temporal_kernel<false, true, false>);
-        carve(temporal_kernel<true, false, false>); carve(temporal_kernel<true, true, false>);
-        carve(variance_sparse_kernel<false, true>); carve(variance_sparse_kernel<true, true>);
-        carve(taa_kernel<false>); carve(taa_kernel<true>);
-    }
-#endif
     svgf_ctx *c = new (std::nothrow) svgf_ctx();
     if (!c) return SVGF_CUDA_ERROR;
     c->device = device; c->W = width; c->H = height; c->storage = storage;

@@ -196,6 +196,28 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
+// 1 / sqrt(x) and 1 / x on the MUFU for arguments that are normal numbers at every call site (1e-10 + variance >= 1e-10;
+// a weight sum >= 1): rsqrtf() / __frcp_rn() spend a dozen instructions on denormal scaling and an exactly rounded
+// reciprocal that a 1-ulp result (1.2e-7 relative, against the 1e-4 parity bar) does not need.
+__device__ __forceinline__ float fast_rsqrt(float x) {
+#if SVGF_EXP == 6
+    return rsqrtf(x);
+#else
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#endif
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+#if SVGF_EXP == 6
+    return __frcp_rn(x);
+#else
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#endif
+}
+
 // read-only, L1-allocating vector loads
 template <typename T> __device__ __forceinline__ T ldg(const T *p) { return __ldg(p); }
 

@@ -59,7 +59,7 @@ __device__ __forceinline__ void fused_task(const AtrousTiledArgs &a, float kZ_sc
         live0[j] = inside && (g0.x != kBackgroundZ);
         live1[j] = inside && (g0.y != kBackgroundZ);
         any_live |= live0[j] | live1[j];
-        C[j].kL = make_float2(a.kL_scale * rsqrtf(1e-10f + c1.z), a.kL_scale * rsqrtf(1e-10f + c1.w));
+        C[j].kL = make_float2(a.kL_scale * fast_rsqrt(1e-10f + c1.z), a.kL_scale * fast_rsqrt(1e-10f + c1.w));
         float2 dz = make_float2(0.f, 0.f);
         if (inside) dz = __ldg(reinterpret_cast<const float2 *>(guide_dz + (size_t)gy * a.W + gx));
         C[j].kZ = make_float2(__fdividef(kZ_scale, fmaxf(dz.x, 1e-6f)), __fdividef(kZ_scale, fmaxf(dz.y, 1e-6f)));
@@ -72,7 +72,7 @@ __device__ __forceinline__ void fused_task(const AtrousTiledArgs &a, float kZ_sc
     for (int j = 0; j < kPkRows; j++) {
         const int si = (row0 + j) * PITCH + pcol;
         const float4 c0 = sC0[si], c1 = sC1[si];
-        const float i0 = __frcp_rn(A[j].S.x), i1 = __frcp_rn(A[j].S.y);
+        const float i0 = fast_rcp(A[j].S.x), i1 = fast_rcp(A[j].S.y);
         o0[j] = make_float4(A[j].r.x * i0, A[j].g.x * i0, A[j].b.x * i0, A[j].v.x * (i0 * i0));
         o1[j] = make_float4(A[j].r.y * i1, A[j].g.y * i1, A[j].b.y * i1, A[j].v.y * (i1 * i1));
         if (!live0[j]) o0[j] = make_float4(c0.x, c0.z, c1.x, c1.z);

@@ -283,7 +283,7 @@ atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_cons
         live0[j] = inside && (lz.z != kBackgroundZ);                               // :554: background passes through
         live1[j] = inside && (lz.w != kBackgroundZ);
         any_live |= live0[j] | live1[j];
-        C[j].kL = make_float2(a.kL_scale * rsqrtf(1e-10f + c1.z), a.kL_scale * rsqrtf(1e-10f + c1.w));   // :562
+        C[j].kL = make_float2(a.kL_scale * fast_rsqrt(1e-10f + c1.z), a.kL_scale * fast_rsqrt(1e-10f + c1.w));   // :562
         C[j].kZ = make_float2(__fdividef(a.kZ_scale, fmaxf(dz[j].x, 1e-6f)), __fdividef(a.kZ_scale, fmaxf(dz[j].y, 1e-6f)));   // :563
         N[j].nx = N[j].ny = N[j].nz = make_float2(0.f, 0.f);
     }
@@ -308,7 +308,7 @@ atrous_lattice_kernel(const __grid_constant__ CUtensorMap mC0, const __grid_cons
         const int gy = y0 + (tg * kPkRows + j) * STEP;
         if (gx >= a.W || gy >= a.H) continue;
         const int si = (row0 + j) * G::pairs + pcol;
-        const float i0 = __frcp_rn(A[j].S.x), i1 = __frcp_rn(A[j].S.y);
+        const float i0 = fast_rcp(A[j].S.x), i1 = fast_rcp(A[j].S.y);
         float4 o0 = make_float4(A[j].r.x * i0, A[j].g.x * i0, A[j].b.x * i0, A[j].v.x * (i0 * i0));
         float4 o1 = make_float4(A[j].r.y * i1, A[j].g.y * i1, A[j].b.y * i1, A[j].v.y * (i1 * i1));
         if (!(live0[j] && live1[j])) {

@@ -342,7 +342,7 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
         any_live |= live0[j] | live1[j];
         float2 var = A[j].v;                                                        // :547 / the pre-blurred plane (GAUSS3)
         if (PREF && inside) var = __ldg(reinterpret_cast<const float2 *>(a.var_blur + (size_t)gy * a.W + gx));
-        C[j].kL = make_float2(a.kL_scale * rsqrtf(1e-10f + var.x), a.kL_scale * rsqrtf(1e-10f + var.y));   // :562
+        C[j].kL = make_float2(a.kL_scale * fast_rsqrt(1e-10f + var.x), a.kL_scale * fast_rsqrt(1e-10f + var.y));   // :562
         float2 dz = make_float2(0.f, 0.f);
         if (inside) dz = __ldg(reinterpret_cast<const float2 *>(guide_dz + (size_t)gy * a.W + gx));
         C[j].kZ = make_float2(__fdividef(a.kZ_scale, fmaxf(dz.x, 1e-6f)), __fdividef(a.kZ_scale, fmaxf(dz.y, 1e-6f)));   // :563
@@ -362,7 +362,7 @@ atrous_packed_kernel(AtrousTiledArgs a, const float4 *__restrict__ guide_n, cons
         const int si = (row0 + j) * G::pairs + pcol;
         float2 cr, cg, cb, cv;
         pk_load_colour<HC>(sC0, sC1, si, cr, cg, cb, cv);
-        const float i0 = __frcp_rn(A[j].S.x), i1 = __frcp_rn(A[j].S.y);
+        const float i0 = fast_rcp(A[j].S.x), i1 = fast_rcp(A[j].S.y);
         float4 o0 = make_float4(A[j].r.x * i0, A[j].g.x * i0, A[j].b.x * i0, A[j].v.x * (i0 * i0));
         float4 o1 = make_float4(A[j].r.y * i1, A[j].g.y * i1, A[j].b.y * i1, A[j].v.y * (i1 * i1));
         if (!live0[j]) o0 = make_float4(cr.x, cg.x, cb.x, cv.x);                     // :556 (clamped centre)

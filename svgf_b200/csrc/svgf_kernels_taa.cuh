@@ -45,12 +45,65 @@ __device__ __forceinline__ int taa_texel(float uv, int size) {
     return min(max(t, 0), size - 1);
 }
 
+constexpr int kTaaBW = 32, kTaaBH = 16, kTaaTW = kTaaBW + 4, kTaaTH = kTaaBH + 4;
+
+// One output pixel.  WINDOW: all nine taps come from the block's shared-memory window (row / column offsets computed once,
+// one add per tap); otherwise from global memory (a block whose window test failed - never, up to float rounding).
+template <bool F32, bool WINDOW>
+__device__ __forceinline__ void taa_pixel(int W, int x, int y, const int (&xs)[3], const int (&ys)[3], int tx0, int ty0, const float4 *sYuv,
+                                          const float4 *sSq, const typename ColourPlane<F32>::texel *__restrict__ filtered,
+                                          const typename ColourPlane<F32>::texel *__restrict__ history,
+                                          typename ColourPlane<F32>::texel *__restrict__ out) {
+    const int col[3] = {xs[0] - tx0, xs[1] - tx0, xs[2] - tx0};
+    const int row[3] = {(ys[0] - ty0) * kTaaTW, (ys[1] - ty0) * kTaaTW, (ys[2] - ty0) * kTaaTW};
+    // encoded texel (ix, iy) of the neighbourhood, and optionally its squared rgb
+    auto tap = [&](int ix, int iy, float4 *sq) -> float4 {
+        if (WINDOW) {
+            const int li = row[iy] + col[ix];
+            if (sq) *sq = sSq[li];
+            return sYuv[li];
+        }
+        const float4 c = clamp01(ColourPlane<F32>::decode(__ldg(filtered + (size_t)ys[iy] * W + xs[ix])));
+        const float r = __fmul_rn(c.x, c.x), g = __fmul_rn(c.y, c.y), b = __fmul_rn(c.z, c.z);
+        if (sq) *sq = make_float4(r, g, b, 0.f);
+        return make_float4(taa_dot3(r, g, b, 0.299f, 0.587f, 0.114f), taa_dot3(r, g, b, -0.14713f, -0.28886f, 0.436f),
+                           taa_dot3(r, g, b, 0.615f, -0.51499f, -0.10001f), 0.f);
+    };
+    const float4 last = clamp01(ColourPlane<F32>::decode(__ldg(history + (size_t)ys[1] * W + xs[1])));   // :299
+    float4 c0sq;
+    const float4 e0 = tap(1, 1, &c0sq);                                              // :306
+    const float rate = fminf(last.w, 0.5f);                                          // :302
+    float3 aa = make_float3(mix_rn(__fmul_rn(last.x, last.x), c0sq.x, rate), mix_rn(__fmul_rn(last.y, last.y), c0sq.y, rate),
+                            mix_rn(__fmul_rn(last.z, last.z), c0sq.z, rate));       // :308
+    aa = taa_encode_pal_yuv(make_float3(__fsqrt_rn(aa.x), __fsqrt_rn(aa.y), __fsqrt_rn(aa.z)));   // :309,:320
+    // plus-shaped box (in0..in4), then the diagonal texels (in5..in8) folded in: :331-336
+    float3 mn = make_float3(e0.x, e0.y, e0.z), mx = mn;
+    auto fold = [&](int ix, int iy, float3 &lo, float3 &hi) {
+        const float4 e = tap(ix, iy, nullptr);
+        lo = make_float3(fminf(lo.x, e.x), fminf(lo.y, e.y), fminf(lo.z, e.z));
+        hi = make_float3(fmaxf(hi.x, e.x), fmaxf(hi.y, e.y), fmaxf(hi.z, e.z));
+    };
+    fold(2, 1, mn, mx); fold(0, 1, mn, mx); fold(1, 2, mn, mx); fold(1, 0, mn, mx);
+    float3 mn2 = mn, mx2 = mx;
+    fold(2, 2, mn2, mx2); fold(0, 2, mn2, mx2); fold(2, 0, mn2, mx2); fold(0, 0, mn2, mx2);
+    auto half_mix = [](float a, float b) { return __fadd_rn(0.5f * a, 0.5f * b); };   // exact halves, one rounding: == the reference's FP64 mix
+    mn = make_float3(half_mix(mn.x, mn2.x), half_mix(mn.y, mn2.y), half_mix(mn.z, mn2.z));
+    mx = make_float3(half_mix(mx.x, mx2.x), half_mix(mx.y, mx2.y), half_mix(mx.z, mx2.z));
+    aa = make_float3(fminf(fmaxf(aa.x, mn.x), mx.x), fminf(fmaxf(aa.y, mn.y), mx.y), fminf(fmaxf(aa.z, mn.z), mx.z));   // :339
+    // decodePalYuv :277-285
+    float3 rgb = make_float3(taa_dot3(aa.x, aa.y, aa.z, 1.0f, 0.0f, 1.13983f), taa_dot3(aa.x, aa.y, aa.z, 1.0f, -0.39465f, -0.58060f),
+                             taa_dot3(aa.x, aa.y, aa.z, 1.0f, 2.03211f, 0.0f));
+    rgb = make_float3(taa_sqrt(rgb.x), taa_sqrt(rgb.y), taa_sqrt(rgb.z));
+    if (rgb.x != rgb.x || rgb.y != rgb.y || rgb.z != rgb.z) rgb = make_float3(0.f, 0.f, 0.f);   // :351
+    const float4 o = make_float4(taa_to_srgb(rgb.x), taa_to_srgb(rgb.y), taa_to_srgb(rgb.z), 1.0f);   // :353
+    out[(size_t)y * W + x] = ColourPlane<F32>::encode(clamp01(o));                   // :355 imageStore
+}
+
 // Block = 32 x 16 outputs.  The block's source texels (its outputs' floor texels and their neighbours: a 36 x 20 window
 // starting two texels up-left of the block, see taa_texel) are loaded, clamped and PAL-YUV-encoded ONCE into shared memory -
 // each is the neighbour of nine outputs - together with their squared rgb (the blend operand of the centre tap).  A tap
 // that falls outside the window (it cannot, up to float rounding of the uv arithmetic at the clamped image borders, which
 // the window covers) is evaluated from global memory instead, so the window size is an optimisation, not an assumption.
-constexpr int kTaaBW = 32, kTaaBH = 16, kTaaTW = kTaaBW + 4, kTaaTH = kTaaBH + 4;
 
 template <bool F32>
 __global__ void __launch_bounds__(kTaaBW *kTaaBH)
@@ -94,47 +147,10 @@ taa_kernel(int W, int H, const typename ColourPlane<F32>::texel *__restrict__ fi
     if (x >= W || y >= H) return;
     const int xs[3] = {sXs[0][cxl], sXs[1][cxl], sXs[2][cxl]};
     const int ys[3] = {sYs[0][cyl], sYs[1][cyl], sYs[2][cyl]};
-    // encoded texel (ix, iy) of the neighbourhood, and optionally its squared rgb
-    auto tap = [&](int ix, int iy, float4 *sq) -> float4 {
-        if (window_ok) {
-            const int li = (ys[iy] - ty0) * kTaaTW + (xs[ix] - tx0);
-            if (sq) *sq = sSq[li];
-            return sYuv[li];
-        }
-        const float4 c = clamp01(ColourPlane<F32>::decode(__ldg(filtered + (size_t)ys[iy] * W + xs[ix])));
-        const float r = __fmul_rn(c.x, c.x), g = __fmul_rn(c.y, c.y), b = __fmul_rn(c.z, c.z);
-        if (sq) *sq = make_float4(r, g, b, 0.f);
-        return make_float4(taa_dot3(r, g, b, 0.299f, 0.587f, 0.114f), taa_dot3(r, g, b, -0.14713f, -0.28886f, 0.436f),
-                           taa_dot3(r, g, b, 0.615f, -0.51499f, -0.10001f), 0.f);
-    };
-    const float4 last = clamp01(ColourPlane<F32>::decode(__ldg(history + (size_t)ys[1] * W + xs[1])));   // :299
-    float4 c0sq;
-    const float4 e0 = tap(1, 1, &c0sq);                                              // :306
-    const float rate = fminf(last.w, 0.5f);                                          // :302
-    float3 aa = make_float3(mix_rn(__fmul_rn(last.x, last.x), c0sq.x, rate), mix_rn(__fmul_rn(last.y, last.y), c0sq.y, rate),
-                            mix_rn(__fmul_rn(last.z, last.z), c0sq.z, rate));       // :308
-    aa = taa_encode_pal_yuv(make_float3(__fsqrt_rn(aa.x), __fsqrt_rn(aa.y), __fsqrt_rn(aa.z)));   // :309,:320
-    // plus-shaped box (in0..in4), then the diagonal texels (in5..in8) folded in: :331-336
-    float3 mn = make_float3(e0.x, e0.y, e0.z), mx = mn;
-    auto fold = [&](int ix, int iy, float3 &lo, float3 &hi) {
-        const float4 e = tap(ix, iy, nullptr);
-        lo = make_float3(fminf(lo.x, e.x), fminf(lo.y, e.y), fminf(lo.z, e.z));
-        hi = make_float3(fmaxf(hi.x, e.x), fmaxf(hi.y, e.y), fmaxf(hi.z, e.z));
-    };
-    fold(2, 1, mn, mx); fold(0, 1, mn, mx); fold(1, 2, mn, mx); fold(1, 0, mn, mx);
-    float3 mn2 = mn, mx2 = mx;
-    fold(2, 2, mn2, mx2); fold(0, 2, mn2, mx2); fold(2, 0, mn2, mx2); fold(0, 0, mn2, mx2);
-    auto half_mix = [](float a, float b) { return __fadd_rn(0.5f * a, 0.5f * b); };   // exact halves, one rounding: == the reference's FP64 mix
-    mn = make_float3(half_mix(mn.x, mn2.x), half_mix(mn.y, mn2.y), half_mix(mn.z, mn2.z));
-    mx = make_float3(half_mix(mx.x, mx2.x), half_mix(mx.y, mx2.y), half_mix(mx.z, mx2.z));
-    aa = make_float3(fminf(fmaxf(aa.x, mn.x), mx.x), fminf(fmaxf(aa.y, mn.y), mx.y), fminf(fmaxf(aa.z, mn.z), mx.z));   // :339
-    // decodePalYuv :277-285
-    float3 rgb = make_float3(taa_dot3(aa.x, aa.y, aa.z, 1.0f, 0.0f, 1.13983f), taa_dot3(aa.x, aa.y, aa.z, 1.0f, -0.39465f, -0.58060f),
-                             taa_dot3(aa.x, aa.y, aa.z, 1.0f, 2.03211f, 0.0f));
-    rgb = make_float3(taa_sqrt(rgb.x), taa_sqrt(rgb.y), taa_sqrt(rgb.z));
-    if (rgb.x != rgb.x || rgb.y != rgb.y || rgb.z != rgb.z) rgb = make_float3(0.f, 0.f, 0.f);   // :351
-    const float4 o = make_float4(taa_to_srgb(rgb.x), taa_to_srgb(rgb.y), taa_to_srgb(rgb.z), 1.0f);   // :353
-    out[(size_t)y * W + x] = ColourPlane<F32>::encode(clamp01(o));                   // :355 imageStore
+    if (window_ok)
+        taa_pixel<F32, true>(W, x, y, xs, ys, tx0, ty0, sYuv, sSq, filtered, history, out);
+    else
+        taa_pixel<F32, false>(W, x, y, xs, ys, tx0, ty0, sYuv, sSq, filtered, history, out);
 }
 
 }  // namespace svgf
