@@ -12,8 +12,9 @@
 //    (x, x+1) at offset dx*STEP are the stored pair at column x + dx*STEP whenever dx*STEP is even;
 //  * the per-output quantities (centre luminance, depth, normal, the two edge-stopping scales, the five sums) are
 //    natural pairs; per-tap constants (kernel weight, 1/length) are immediates broadcast by the instruction;
-//  * level 0 (STEP = 1) has odd offsets: dx = +-1 taps are evaluated with the scalar form on the halves of the three
-//    aligned pairs that are loaded anyway (dx = -2, 0, +2 stay packed).
+//  * level 0 (STEP = 1) has odd offsets: the dx = +-1 taps of outputs (x, x+1) are packed across the two directions -
+//    (x <- x+1, x+1 <- x) is the centre pair with its halves swapped, (x <- x-1, x+1 <- x+2) is {left pair.hi, right
+//    pair.lo} - at the price of two register moves per operand pair instead of a scalar evaluation per pixel.
 // Everything else follows svgf_kernels_tiled.cuh: one lattice row phase per tile, contiguous 128-pixel x range,
 // R outputs per thread and column for register-level tap reuse, per-pixel work (decode, clamp, luminance) done once
 // at staging, null texels (z = +inf) outside the image.  Arithmetic and rounding are identical to the scalar
@@ -81,7 +82,7 @@ __device__ __forceinline__ void pk_tap2(PkAcc &A, const PkCentre &C, const PkTap
     A.v = __ffma2_rn(__fmul2_rn(w, w), q.v, A.v);
 }
 
-// u and p of one normal pair, scalar, same operations and roundings as the packed tap (and as pk_tap1)
+// u and p of one normal pair, scalar, same operations and roundings as the packed tap
 template <int TERMS>
 __device__ __forceinline__ void pk_normal_term(float nx, float ny, float nz, float qnx, float qny, float qnz, const PkCoef &k,
                                                float &u, float &p) {
@@ -118,22 +119,6 @@ __device__ __forceinline__ void pk_tap2n(PkAcc &A, const PkCentreN &C, const PkT
     A.g = __ffma2_rn(w, q.g, A.g);
     A.b = __ffma2_rn(w, q.b, A.b);
     A.v = __ffma2_rn(__fmul2_rn(w, w), q.v, A.v);
-}
-
-// scalar form for one output and one tap (level 0, odd dx)
-template <int TERMS, bool UNIF = false>
-__device__ __forceinline__ void pk_tap1(float &S, float &Ar, float &Ag, float &Ab, float &Av, float lc, float zc, float nx, float ny,
-                                        float nz, float kL, float kZ, float ql, float qz, float qnx, float qny, float qnz, float qr,
-                                        float qg, float qb, float qv, float ck, float cinv, const PkCoef &k, float un = 0.f,
-                                        float pn = 0.f) {
-    float base = fmaf(fabsf(ql - lc), kL, ck);
-    base = fmaf(fabsf(qz - zc) * kZ, cinv, base);
-    float u = un, p = pn;
-    if (!UNIF) pk_normal_term<TERMS>(nx, ny, nz, qnx, qny, qnz, k, u, p);
-    const float w = fast_exp2(fmaf(-u, p, -base));
-    S += w;
-    Ar = fmaf(w, qr, Ar); Ag = fmaf(w, qg, Ag); Ab = fmaf(w, qb, Ab);
-    Av = fmaf(w * w, qv, Av);
 }
 
 // Colour planes of the tile.  HC = false: two float4 planes {r0,r1,g0,g1} {b0,b1,v0,v1}.  HC = true (fp16 storage only):
@@ -195,39 +180,47 @@ __device__ __forceinline__ void pk_all_taps(PkAcc (&A)[R], const PkCentre (&C)[R
         }
     } else {
         // level 0: the six columns x-2 .. x+3 are the three aligned pairs m = -1, 0, +1.  Pair m serves dx = 2m packed
-        // (outputs x and x+1 tap columns x+2m and x+1+2m) and the odd offsets on its halves: output 0 (column x)
-        // taps x-1 = pair(-1).hi and x+1 = pair(0).hi; output 1 (column x+1) taps x = pair(0).lo and x+2 = pair(+1).lo.
-        // One pair is live at a time.
+        // (outputs x and x+1 tap columns x+2m and x+1+2m).  The odd offsets stay packed as well, by pairing the two outputs
+        // with DIFFERENT dx of the same |dx| = 1 (same kernel weight and length): (x <- x+1, x+1 <- x) is the centre pair
+        // with its halves swapped, (x <- x-1, x+1 <- x+2) is {pair(-1).hi, pair(+1).lo}.  Each lane of a packed operation
+        // is the scalar operation on the same operands, so the results are those of the scalar form.
+        auto load_pair = [&](int si, PkTap &q) {
+            float4 g0, g1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (UNIF) { const float2 zz = *reinterpret_cast<const float2 *>(&sG0[si]); g0 = make_float4(zz.x, zz.y, 0.f, 0.f); }
+            else { g0 = sG0[si]; g1 = sG1[si]; }
+            pk_load_colour<HC>(sC0, sC1, si, q.r, q.g, q.b, q.v);
+            q.z = make_float2(g0.x, g0.y); q.nx = make_float2(g0.z, g0.w); q.ny = make_float2(g1.x, g1.y); q.nz = make_float2(g1.z, g1.w);
+            q.l = sL[si];
+        };
+        auto halves = [](const float2 &lo_src, const float2 &hi_src) { return make_float2(lo_src.y, hi_src.x); };   // {a.hi, b.lo}
+        auto cross = [&](const PkTap &a, const PkTap &b) {
+            PkTap q;
+            q.r = halves(a.r, b.r); q.g = halves(a.g, b.g); q.b = halves(a.b, b.b); q.v = halves(a.v, b.v);
+            q.l = halves(a.l, b.l); q.z = halves(a.z, b.z);
+            q.nx = halves(a.nx, b.nx); q.ny = halves(a.ny, b.ny); q.nz = halves(a.nz, b.nz);
+            return q;
+        };
+        auto row_taps = [&](const PkTap &q, int t, int ax, bool skip_centre) {
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const int dy = t - j;
+                if (dy < -2 || dy > 2 || (skip_centre && dy == 0)) continue;
+                const int ay = dy < 0 ? -dy : dy;
+                pk_tap2<TERMS, UNIF>(A[j], C[j], q, tap_neg_log2_kernel(ax, ay), tap_inv_len(ax, ay), k, un, pn);
+            }
+        };
 #pragma unroll
         for (int t = -2; t < R + 2; t++) {
-#pragma unroll
-            for (int m = -1; m <= 1; m++) {
-                const int si = (row0 + t) * G::pairs + pcol + m;
-                float4 g0, g1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (UNIF) { const float2 zz = *reinterpret_cast<const float2 *>(&sG0[si]); g0 = make_float4(zz.x, zz.y, 0.f, 0.f); }
-                else { g0 = sG0[si]; g1 = sG1[si]; }
-                PkTap q;
-                pk_load_colour<HC>(sC0, sC1, si, q.r, q.g, q.b, q.v);
-                q.z = make_float2(g0.x, g0.y); q.nx = make_float2(g0.z, g0.w); q.ny = make_float2(g1.x, g1.y); q.nz = make_float2(g1.z, g1.w);
-                q.l = sL[si];
-#pragma unroll
-                for (int j = 0; j < R; j++) {
-                    const int dy = t - j;
-                    if (dy < -2 || dy > 2) continue;
-                    const int ay = dy < 0 ? -dy : dy;
-                    if (!(m == 0 && dy == 0))
-                        pk_tap2<TERMS, UNIF>(A[j], C[j], q, tap_neg_log2_kernel(m == 0 ? 0 : 2, ay), tap_inv_len(m == 0 ? 0 : 2, ay), k, un, pn);
-                    const float ck = tap_neg_log2_kernel(1, ay), ci = tap_inv_len(1, ay);
-                    if (m <= 0)   // output 0 <- this pair's hi half (x-1 for m = -1, x+1 for m = 0)
-                        pk_tap1<TERMS, UNIF>(A[j].S.x, A[j].r.x, A[j].g.x, A[j].b.x, A[j].v.x, C[j].lc.x, C[j].zc.x, C[j].nx.x, C[j].ny.x,
-                                       C[j].nz.x, C[j].kL.x, C[j].kZ.x, q.l.y, q.z.y, q.nx.y, q.ny.y, q.nz.y, q.r.y, q.g.y, q.b.y, q.v.y,
-                                       ck, ci, k, un, pn);
-                    if (m >= 0)   // output 1 <- this pair's lo half (x for m = 0, x+2 for m = +1)
-                        pk_tap1<TERMS, UNIF>(A[j].S.y, A[j].r.y, A[j].g.y, A[j].b.y, A[j].v.y, C[j].lc.y, C[j].zc.y, C[j].nx.y, C[j].ny.y,
-                                       C[j].nz.y, C[j].kL.y, C[j].kZ.y, q.l.x, q.z.x, q.nx.x, q.ny.x, q.nz.x, q.r.x, q.g.x, q.b.x, q.v.x,
-                                       ck, ci, k, un, pn);
-                }
-            }
+            const int si = (row0 + t) * G::pairs + pcol;
+            PkTap q0, qa, qb;
+            load_pair(si, q0);
+            row_taps(q0, t, 0, true);                       // dx = 0
+            row_taps(cross(q0, q0), t, 1, false);           // x <- x+1, x+1 <- x
+            load_pair(si - 1, qa);
+            row_taps(qa, t, 2, false);                      // dx = -2
+            load_pair(si + 1, qb);
+            row_taps(qb, t, 2, false);                      // dx = +2
+            row_taps(cross(qa, qb), t, 1, false);           // x <- x-1, x+1 <- x+2
         }
     }
 }
