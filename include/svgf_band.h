@@ -56,6 +56,18 @@ svgf_status svgf_band_reset(svgf_band *b, const svgf_frame_buffers *bufs, void *
 svgf_status svgf_band_frame(svgf_band *b, const svgf_params *params, const svgf_gbuffer gbuf[2], const svgf_frame_buffers *bufs,
                             void *stream);
 
+/* The same frame with ALL bands inside one process - one thread driving several GPUs, or (tests) every band on one GPU: no
+ * NCCL; a band's aprons are refreshed by cudaMemcpyPeerAsync from its neighbours' planes on the band's own side stream,
+ * ordered by events.  svgf_band_create_group creates the `world` bands (devices[g] = CUDA device of band g; destroy each
+ * with svgf_band_destroy; svgf_band_rows / reset / sync / launch_count work per band).  svgf_band_group_frame issues one
+ * frame of every band: gbufs[2 * g + k] = G-buffer k of band g, bufs[g], streams[g].  The schedule per band is that of
+ * svgf_band_frame (same plan, same kernels, same row ranges); the bands advance together from exchange to exchange.
+ * Results are bit-identical to svgf_band_frame over NCCL and to the whole frame on one GPU. */
+svgf_status svgf_band_create_group(svgf_band **out, const int32_t *devices, int world, int width, int full_height, svgf_storage storage,
+                                   const int32_t *row_bounds);
+svgf_status svgf_band_group_frame(svgf_band *const *bands, int world, const svgf_params *params, const svgf_gbuffer *gbufs,
+                                  const svgf_frame_buffers *bufs, void *const *streams);
+
 /* Makes `stream` wait for every exchange this driver has posted (before reading state planes from outside). */
 svgf_status svgf_band_sync(svgf_band *b, void *stream);
 

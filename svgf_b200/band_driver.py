@@ -32,19 +32,23 @@ def broadcast_unique_id(rank, src=0, group=None, device=None):
 
 
 class BandDriver:
-    def __init__(self, width, height, rank, world, device, storage="f16", levels=5, bounds=None, unique_id=None, group=None):
+    def __init__(self, width, height, rank, world, device, storage="f16", levels=5, bounds=None, unique_id=None, group=None,
+                 _handle=None):
         self.lib = _lib.lib()
         self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
         self.rank, self.world, self.Width, self.FullHeight = rank, world, int(width), int(height)
-        if world > 1 and unique_id is None:
-            unique_id = broadcast_unique_id(rank, group=group, device=self.device)
-        uid = (C.c_ubyte * 128)(*unique_id) if unique_id is not None else None
-        rb = (C.c_int32 * (world + 1))(*bounds) if bounds is not None else None
-        self._h = C.c_void_p()
-        st = self.lib.svgf_band_create(C.byref(self._h), self.device.index or 0, rank, world, self.Width, self.FullHeight,
-                                       {"f16": _lib.SVGF_STORE_F16, "f32": _lib.SVGF_STORE_F32}[storage], uid, rb)
-        if st != _lib.SVGF_OK:
-            raise SvgfError(st, "svgf_band_create")
+        if _handle is not None:                                # a member of a BandGroup: the group created the native band
+            self._h = _handle
+        else:
+            if world > 1 and unique_id is None:
+                unique_id = broadcast_unique_id(rank, group=group, device=self.device)
+            uid = (C.c_ubyte * 128)(*unique_id) if unique_id is not None else None
+            rb = (C.c_int32 * (world + 1))(*bounds) if bounds is not None else None
+            self._h = C.c_void_p()
+            st = self.lib.svgf_band_create(C.byref(self._h), self.device.index or 0, rank, world, self.Width, self.FullHeight,
+                                           {"f16": _lib.SVGF_STORE_F16, "f32": _lib.SVGF_STORE_F32}[storage], uid, rb)
+            if st != _lib.SVGF_OK:
+                raise SvgfError(st, "svgf_band_create")
         rows = (C.c_int32 * 4)()
         self.lib.svgf_band_rows(self._h, C.byref(rows))
         self.y0, self.y1, self.ly0, self.ly1 = (int(v) for v in rows)
@@ -119,3 +123,68 @@ class BandDriver:
             self.close()
         except Exception:
             pass
+
+
+class BandGroup:
+    """All bands of one frame inside this process (svgf_band_create_group / svgf_band_group_frame): band g on devices[g] -
+    several GPUs driven by one thread, or every band on the same GPU, which is how the band schedule (plan, row-block ranges,
+    halo and state exchanges) is tested bit for bit on a one-GPU box.  Halos travel by cudaMemcpyPeerAsync, not NCCL.
+    ``bands[g]`` is a BandDriver for band g's local image (fill its Framebuffer / RenderBuffer rows, read result_band());
+    ``Filter()`` / ``EndFrame()`` / ``Reset()`` act on all bands."""
+
+    def __init__(self, width, height, devices, storage="f16", levels=5, bounds=None):
+        self.lib = _lib.lib()
+        world = len(devices)
+        devs = [torch.device("cuda", d) if not isinstance(d, torch.device) else d for d in devices]
+        hs = (C.c_void_p * world)()
+        dv = (C.c_int32 * world)(*[d.index or 0 for d in devs])
+        rb = (C.c_int32 * (world + 1))(*bounds) if bounds is not None else None
+        st = self.lib.svgf_band_create_group(hs, dv, world, int(width), int(height),
+                                             {"f16": _lib.SVGF_STORE_F16, "f32": _lib.SVGF_STORE_F32}[storage], rb)
+        if st != _lib.SVGF_OK:
+            raise SvgfError(st, "svgf_band_create_group")
+        self.world = world
+        self.bands = [BandDriver(width, height, g, world, devs[g], storage=storage, levels=levels, _handle=C.c_void_p(hs[g]))
+                      for g in range(world)]
+        self.params = _lib.default_params()
+        self.params.atrous_iterations = levels
+        self.streams = None          # optional: one torch.cuda.Stream per band (default: each device's current stream)
+
+    def Reset(self):
+        for b in self.bands:
+            b.Reset()
+
+    def Filter(self):
+        if self.streams is None:
+            return self._filter([b._stream() for b in self.bands])
+        for b, s in zip(self.bands, self.streams):
+            s.wait_stream(torch.cuda.current_stream(b.device))
+        self._filter([C.c_void_p(s.cuda_stream) for s in self.streams])
+        for b, s in zip(self.bands, self.streams):
+            torch.cuda.current_stream(b.device).wait_stream(s)
+
+    def _filter(self, stream_ptrs):
+        w = self.world
+        hs = (C.c_void_p * w)(*[b._h for b in self.bands])
+        g = (SvgfGBuffer * (2 * w))()
+        bufs = (SvgfFrameBuffers * w)()
+        streams = (C.c_void_p * w)()
+        for i, b in enumerate(self.bands):
+            g[2 * i], g[2 * i + 1] = b.Framebuffer[0].as_struct(), b.Framebuffer[1].as_struct()
+            bufs[i] = b._bufs()
+            streams[i] = stream_ptrs[i]
+        st = self.lib.svgf_band_group_frame(hs, w, C.byref(self.params), g, bufs, streams)
+        if st != _lib.SVGF_OK:
+            raise SvgfError(st, "svgf_band_group_frame", max(self.lib.svgf_band_last_error(b._h) for b in self.bands))
+
+    def EndFrame(self):
+        for b in self.bands:
+            b.EndFrame()
+
+    def sync(self):
+        for b in self.bands:
+            b.sync()
+
+    def close(self):
+        for b in self.bands:
+            b.close()

@@ -66,6 +66,7 @@ struct Plane {          // rows of a local image as one contiguous run per row r
     char *base;         // address of local row 0
     size_t row_bytes;
 };
+struct PlaneSet { const Plane *planes; int n; int rows; };
 
 }  // namespace
 
@@ -79,6 +80,26 @@ struct svgf_band {
     bool state_pending = false;
     bool dry_run = false;          // SVGF_FLAG_BAND_NO_EXCHANGE of the current call
     int last_err = 0;
+    // in-process group (svgf_band_create_group): the neighbours' bands; halos are copied from their planes
+    bool in_group = false;
+    svgf_band *up = nullptr, *down = nullptr;
+
+    // ---- the frame in flight: svgf_band_frame / svgf_band_group_frame advance it from exchange to exchange ----
+    struct Frame {
+        svgf_params params;
+        svgf_frame_buffers bufs;
+        cudaStream_t s = nullptr;
+        int N = 0, slot = 0, src = 0, cur_level = 1, n_halo = 0, n_steps = 0, pc = 0, last_exchange = -1;
+        svgf_band_step steps[32];
+        Plane state[3];                // colour history, moments, history lengths of this frame (the next frame's previous state)
+        // the exchange the frame is stopped at: up to two plane sets (lattice planes of a level, state planes)
+        Plane lattice[3];
+        PlaneSet sets[2];
+        int n_sets = 0;
+        cudaEvent_t ready = nullptr;   // recorded on the main stream: the rows this exchange sends are final
+        cudaEvent_t done = nullptr;    // to record on the side stream after the exchange (null: none)
+        bool carries_state = false;
+    } f;
 
     int band_lo() const { return y0 - ly0; }     // local row of the first owned row
     int band_hi() const { return y1 - ly0; }     // local row one past the last owned row
@@ -105,7 +126,6 @@ svgf_status band_nccl(svgf_band *b, int r) {
 
 // Refresh the apron rows on each side of the band with the neighbours' band rows, for every plane of up to two plane sets
 // (each with its own row count): ONE grouped send/recv on the side stream.
-struct PlaneSet { const Plane *planes; int n; int rows; };
 svgf_status exchange(svgf_band *b, const PlaneSet *sets, int n_sets) {
     if (b->dry_run) return SVGF_OK;
     const NcclApi &n = nccl();
@@ -126,6 +146,31 @@ svgf_status exchange(svgf_band *b, const PlaneSet *sets, int n_sets) {
             }
         }
     return band_nccl(b, n.GroupEnd());
+}
+
+// The same refresh inside an in-process group: the neighbours' band rows are COPIED from their planes (same plane order,
+// same row pitch) into this band's aprons on this band's side stream.  The caller has made the side stream wait for the
+// neighbours' `ready` events.  cudaMemcpyPeerAsync: the bands may live on different devices or all on one.
+svgf_status exchange_copy(svgf_band *b) {
+    if (b->dry_run) return SVGF_OK;
+    const int lo = b->band_lo(), hi = b->band_hi();
+    for (int q = 0; q < b->f.n_sets; q++)
+        for (int k = 0; k < b->f.sets[q].n; k++) {
+            const Plane &p = b->f.sets[q].planes[k];
+            const int rows = b->f.sets[q].rows;
+            const size_t bytes = (size_t)rows * p.row_bytes;
+            if (b->up) {
+                const Plane &o = b->up->f.sets[q].planes[k];
+                BAND_TRY(band_cuda(b, cudaMemcpyPeerAsync(p.base + (size_t)(lo - rows) * p.row_bytes, b->device,
+                                                          o.base + (size_t)(b->up->band_hi() - rows) * o.row_bytes, b->up->device, bytes, b->side)));
+            }
+            if (b->down) {
+                const Plane &o = b->down->f.sets[q].planes[k];
+                BAND_TRY(band_cuda(b, cudaMemcpyPeerAsync(p.base + (size_t)hi * p.row_bytes, b->device,
+                                                          o.base + (size_t)b->down->band_lo() * o.row_bytes, b->down->device, bytes, b->side)));
+            }
+        }
+    return SVGF_OK;
 }
 
 }  // namespace
@@ -188,10 +233,10 @@ svgf_status svgf_band_unique_id(void *id_out) {
     return SVGF_OK;
 }
 
-svgf_status svgf_band_create(svgf_band **out, int device, int rank, int world, int width, int full_height, svgf_storage storage,
-                             const void *unique_id, const int32_t *row_bounds) {
+static svgf_status band_create(svgf_band **out, int device, int rank, int world, int width, int full_height, svgf_storage storage,
+                               const void *unique_id, const int32_t *row_bounds, bool in_group) {
     if (!out || world < 1 || rank < 0 || rank >= world || width <= 0 || full_height <= 0) return SVGF_INVALID_ARG;
-    if (world > 1 && !unique_id) return SVGF_INVALID_ARG;
+    if (world > 1 && !unique_id && !in_group) return SVGF_INVALID_ARG;
     *out = nullptr;
     int y0, y1;
     if (row_bounds) {
@@ -208,10 +253,11 @@ svgf_status svgf_band_create(svgf_band **out, int device, int rank, int world, i
         y1 = y0 + base + (rank < rem ? 1 : 0);
         if (world > 1 && base < SVGF_BAND_APRON) return SVGF_UNSUPPORTED;
     }
-    if (world > 1 && !nccl().ok) return SVGF_UNSUPPORTED;
+    if (world > 1 && !in_group && !nccl().ok) return SVGF_UNSUPPORTED;
     svgf_band *b = new (std::nothrow) svgf_band();
     if (!b) return SVGF_CUDA_ERROR;
     b->device = device; b->rank = rank; b->world = world; b->W = width; b->H = full_height;
+    b->in_group = in_group;
     b->y0 = y0; b->y1 = y1;
     b->ly0 = (world > 1 && y0 - SVGF_BAND_APRON > 0) ? y0 - SVGF_BAND_APRON : (world > 1 ? 0 : y0);
     b->ly1 = (world > 1 && y1 + SVGF_BAND_APRON < full_height) ? y1 + SVGF_BAND_APRON : (world > 1 ? full_height : y1);
@@ -231,7 +277,7 @@ svgf_status svgf_band_create(svgf_band **out, int device, int rank, int world, i
     for (cudaEvent_t *ev : evs)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     int nr = 0;
-    if (e == cudaSuccess && world > 1) {
+    if (e == cudaSuccess && world > 1 && !in_group) {
         NcclUniqueId id;
         std::memcpy(&id, unique_id, sizeof(id));
         nr = nccl().CommInitRank(&b->comm, world, id, rank);
@@ -242,12 +288,19 @@ svgf_status svgf_band_create(svgf_band **out, int device, int rank, int world, i
     return SVGF_OK;
 }
 
+svgf_status svgf_band_create(svgf_band **out, int device, int rank, int world, int width, int full_height, svgf_storage storage,
+                             const void *unique_id, const int32_t *row_bounds) {
+    return band_create(out, device, rank, world, width, full_height, storage, unique_id, row_bounds, false);
+}
+
 void svgf_band_destroy(svgf_band *b) {
     if (!b) return;
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(b->device);
     if (b->side) cudaStreamSynchronize(b->side);
+    if (b->up) { cudaStreamSynchronize(b->up->side); b->up->down = nullptr; }       // a neighbour's copies read this band's planes
+    if (b->down) { cudaStreamSynchronize(b->down->side); b->down->up = nullptr; }
     if (b->comm) nccl().CommDestroy(b->comm);
     if (b->side) cudaStreamDestroy(b->side);
     cudaEvent_t evs[] = {b->ev_l0, b->ev_boundary[0], b->ev_boundary[1], b->ev_halo[0], b->ev_halo[1], b->ev_state};
@@ -281,24 +334,30 @@ svgf_status svgf_band_reset(svgf_band *b, const svgf_frame_buffers *bufs, void *
     return svgf_reset(b->ctx, bufs, stream);
 }
 
-svgf_status svgf_band_frame(svgf_band *b, const svgf_params *params, const svgf_gbuffer gbuf[2], const svgf_frame_buffers *bufs,
-                            void *stream) {
-    if (!b || !params || !gbuf || !bufs) return SVGF_INVALID_ARG;
+namespace {
+
+// Everything of the frame up to and including level 0, and the plan of the remaining levels.
+svgf_status frame_begin(svgf_band *b, const svgf_params *params, const svgf_gbuffer gbuf[2], const svgf_frame_buffers *bufs, void *stream) {
     svgf_ctx *c = b->ctx;
-    cudaStream_t s = (cudaStream_t)stream;
+    svgf_band::Frame &f = b->f;
     const int N = params->atrous_iterations;
-    if (b->world == 1) return svgf_frame(c, params, gbuf, bufs, stream);   // one band = the whole frame
     if (N < 2 || N > 5) return SVGF_UNSUPPORTED;
     if (bufs->ping_pong != 0 && bufs->ping_pong != 1) return SVGF_INVALID_ARG;
     const int P = bufs->ping_pong;
+    f.params = *params; f.bufs = *bufs; f.s = (cudaStream_t)stream; f.N = N;
+    cudaStream_t s = f.s;
     b->dry_run = (params->flags & SVGF_FLAG_BAND_NO_EXCHANGE) != 0;
-    int prev_dev = -1;
-    cudaGetDevice(&prev_dev);
-    if (prev_dev != b->device) BAND_TRY(band_cuda(b, cudaSetDevice(b->device)));
-    struct Restore { int d, cur; ~Restore() { if (d >= 0 && d != cur) cudaSetDevice(d); } } restore{prev_dev, b->device};
 
     // previous-frame state in the aprons: posted under the previous frame's levels
     BAND_TRY(svgf_band_sync(b, stream));
+    if (b->in_group) {
+        // a neighbour copies rows out of THIS band's planes on its own side stream: this frame must not overwrite them
+        // before those copies (all posted during the previous group frame) have run
+        for (svgf_band *nb : {b->up, b->down}) {
+            if (!nb) continue;
+            for (cudaEvent_t ev : {nb->ev_halo[0], nb->ev_halo[1], nb->ev_state}) BAND_TRY(band_cuda(b, cudaStreamWaitEvent(s, ev, 0)));
+        }
+    }
 
     // temporal + variance over the whole local image = svgf_frame with no a-trous level (variance output in filter[0])
     svgf_params p0 = *params;
@@ -306,63 +365,172 @@ svgf_status svgf_band_frame(svgf_band *b, const svgf_params *params, const svgf_
     BAND_TRY(svgf_frame(c, &p0, gbuf, bufs, stream));
     if (!svgf::staged_run_possible(c, params, bufs->filter[0], bufs->filter[1], bufs->render[P], 0, N)) return SVGF_UNSUPPORTED;
     BAND_TRY(svgf::lattice_prepare(c, s));
-    const int slot = c->guide_cur;
+    f.slot = c->guide_cur;
     c->dispatch_n = 0;
 
     // level 0 over the whole local image: it also writes the normal planes every later level reads in the apron, and the
     // colour history of the apron rows is replaced by the neighbours' below
-    BAND_TRY(svgf::staged_level(c, params, slot, 0, 0, bufs->filter[0], 0, nullptr, bufs->render[P], 0, 0, 0, 0, false, s));
+    BAND_TRY(svgf::staged_level(c, params, f.slot, 0, 0, bufs->filter[0], 0, nullptr, bufs->render[P], 0, 0, 0, 0, false, s));
     // next frame's previous-frame state - colour history (level 0's output), moments and history lengths - is final from here
     // on.  It travels with the LAST halo exchange of the frame (one NCCL launch fewer; it is not needed before the next
     // frame's temporal pass), or on its own right away when no level exchanges a halo.
     BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_l0, s)));
     const size_t ct = c->storage == SVGF_STORE_F32 ? 16 : 8, mt = c->storage == SVGF_STORE_F32 ? 8 : 4;
-    const Plane state[3] = {{(char *)bufs->render[P], (size_t)b->W * ct}, {(char *)bufs->moments[P], (size_t)b->W * mt},
-                            {(char *)bufs->history, (size_t)b->W}};
-    const PlaneSet state_set = {state, 3, SVGF_BAND_APRON};
+    f.state[0] = Plane{(char *)bufs->render[P], (size_t)b->W * ct};
+    f.state[1] = Plane{(char *)bufs->moments[P], (size_t)b->W * mt};
+    f.state[2] = Plane{(char *)bufs->history, (size_t)b->W};
 
     // levels 1..N-1 as planned by svgf_band_plan (the same function the CPU tests check)
-    svgf_band_step steps[32];
-    const int n_steps = svgf_band_plan(b->rank, b->world, b->band_lo(), b->band_hi(), b->local_rows(), N, steps, 32);
-    if (n_steps < 0) return SVGF_UNSUPPORTED;
-    int last_exchange = -1;
-    for (int i = 0; i < n_steps; i++)
-        if (steps[i].kind == SVGF_BAND_STEP_EXCHANGE) last_exchange = i;
-    if (last_exchange < 0) {
-        BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, b->ev_l0, 0)));
-        BAND_TRY(exchange(b, &state_set, 1));
-        BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_state, b->side)));
-        b->state_pending = true;
+    f.n_steps = svgf_band_plan(b->rank, b->world, b->band_lo(), b->band_hi(), b->local_rows(), N, f.steps, 32);
+    if (f.n_steps < 0) return SVGF_UNSUPPORTED;
+    f.last_exchange = -1;
+    for (int i = 0; i < f.n_steps; i++)
+        if (f.steps[i].kind == SVGF_BAND_STEP_EXCHANGE) f.last_exchange = i;
+    f.src = 0;                                     // lattice colour set holding the input of the current level
+    f.cur_level = 1; f.n_halo = 0;
+    f.pc = f.last_exchange < 0 ? -1 : 0;           // -1: the state-only exchange comes first
+    return SVGF_OK;
+}
+
+// Runs the frame's steps up to the next exchange.  *stopped = true: f.sets / f.ready / f.done describe the exchange to
+// perform (frame_exchanged() then continues); false: the frame has been issued completely.
+svgf_status frame_run(svgf_band *b, bool *stopped) {
+    svgf_ctx *c = b->ctx;
+    svgf_band::Frame &f = b->f;
+    cudaStream_t s = f.s;
+    *stopped = false;
+    if (f.pc < 0) {                                // no level exchanges a halo: the state travels on its own
+        f.sets[0] = PlaneSet{f.state, 3, SVGF_BAND_APRON};
+        f.n_sets = 1; f.ready = b->ev_l0; f.done = nullptr; f.carries_state = true;
+        *stopped = true;
+        return SVGF_OK;
     }
-    int src = 0;                                   // lattice colour set holding the input of the current level
-    int cur_level = 1, n_halo = 0;
-    for (int i = 0; i < n_steps; i++) {
-        const svgf_band_step &st = steps[i];
-        if (st.level != cur_level) { src = 1 - src; cur_level = st.level; }
-        const bool last = (st.level == N - 1);
+    for (; f.pc < f.n_steps; f.pc++) {
+        const svgf_band_step &st = f.steps[f.pc];
+        if (st.level != f.cur_level) { f.src = 1 - f.src; f.cur_level = st.level; }
+        const bool last = (st.level == f.N - 1);
         if (st.kind == SVGF_BAND_STEP_WAIT_HALO) {
             BAND_TRY(band_cuda(b, cudaStreamWaitEvent(s, b->ev_halo[(st.level - 3) & 1], 0)));
         } else if (st.kind == SVGF_BAND_STEP_LAUNCH) {
-            BAND_TRY(svgf::staged_level(c, params, slot, st.level, last ? 2 : 1, nullptr, src, last ? bufs->filter[0] : nullptr, nullptr,
+            BAND_TRY(svgf::staged_level(c, &f.params, f.slot, st.level, last ? 2 : 1, nullptr, f.src, last ? f.bufs.filter[0] : nullptr, nullptr,
                                         st.yblock0, st.nyblocks, st.yblock1, st.nyblocks1, false, s));
         } else {   // SVGF_BAND_STEP_EXCHANGE: rows of THIS level's output, for level + 1
-            cudaEvent_t evb = b->ev_boundary[n_halo & 1], evh = b->ev_halo[(st.level + 1 - 3) & 1];
-            BAND_TRY(band_cuda(b, cudaEventRecord(evb, s)));
-            BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, evb, 0)));       // (implies level 0: same stream, earlier)
-            const svgf::LatticeColour &dst = c->lat.sc[1 - src];
+            cudaEvent_t evb = b->ev_boundary[f.n_halo & 1];
+            BAND_TRY(band_cuda(b, cudaEventRecord(evb, s)));                   // (implies level 0: same stream, earlier)
+            const svgf::LatticeColour &dst = c->lat.sc[1 - f.src];
             const size_t row_bytes = (size_t)c->lat.pitch_pairs * 16, pad = (size_t)svgf::kLatPadY * row_bytes;
-            const Plane pl[3] = {{(char *)dst.c0 + pad, row_bytes}, {(char *)dst.c1 + pad, row_bytes}, {(char *)dst.lz + pad, row_bytes}};
-            const PlaneSet sets[2] = {{pl, 3, st.rows}, state_set};
-            BAND_TRY(exchange(b, sets, i == last_exchange ? 2 : 1));
-            BAND_TRY(band_cuda(b, cudaEventRecord(evh, b->side)));
-            if (i == last_exchange) {
-                BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_state, b->side)));
-                b->state_pending = true;
-            }
-            n_halo++;
+            f.lattice[0] = Plane{(char *)dst.c0 + pad, row_bytes};
+            f.lattice[1] = Plane{(char *)dst.c1 + pad, row_bytes};
+            f.lattice[2] = Plane{(char *)dst.lz + pad, row_bytes};
+            f.sets[0] = PlaneSet{f.lattice, 3, st.rows};
+            f.sets[1] = PlaneSet{f.state, 3, SVGF_BAND_APRON};
+            f.carries_state = (f.pc == f.last_exchange);
+            f.n_sets = f.carries_state ? 2 : 1;
+            f.ready = evb; f.done = b->ev_halo[(st.level + 1 - 3) & 1];
+            *stopped = true;
+            return SVGF_OK;
         }
     }
     return SVGF_OK;
+}
+
+// The exchange frame_run() stopped at, on the side stream; then the bookkeeping that lets the frame continue.
+svgf_status frame_exchange(svgf_band *b) {
+    svgf_band::Frame &f = b->f;
+    BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, f.ready, 0)));
+    if (b->in_group) {
+        for (svgf_band *nb : {b->up, b->down})
+            if (nb) BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, nb->f.ready, 0)));
+        BAND_TRY(exchange_copy(b));
+    } else {
+        BAND_TRY(exchange(b, f.sets, f.n_sets));
+    }
+    if (f.done) BAND_TRY(band_cuda(b, cudaEventRecord(f.done, b->side)));
+    if (f.carries_state) {
+        BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_state, b->side)));
+        b->state_pending = true;
+    }
+    if (f.pc >= 0) f.n_halo++;
+    f.pc++;                                        // -1 -> 0: the steps follow the state-only exchange
+    return SVGF_OK;
+}
+
+struct DeviceScope {
+    int prev = -1, cur = -1;
+    cudaError_t enter(int device) {
+        cudaGetDevice(&prev);
+        cur = device;
+        return prev != device ? cudaSetDevice(device) : cudaSuccess;
+    }
+    ~DeviceScope() { if (prev >= 0 && prev != cur) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+svgf_status svgf_band_frame(svgf_band *b, const svgf_params *params, const svgf_gbuffer gbuf[2], const svgf_frame_buffers *bufs,
+                            void *stream) {
+    if (!b || !params || !gbuf || !bufs) return SVGF_INVALID_ARG;
+    if (b->in_group) return SVGF_INVALID_ARG;                                  // a group's bands advance together: svgf_band_group_frame
+    if (b->world == 1) return svgf_frame(b->ctx, params, gbuf, bufs, stream);  // one band = the whole frame
+    DeviceScope dev;
+    BAND_TRY(band_cuda(b, dev.enter(b->device)));
+    BAND_TRY(frame_begin(b, params, gbuf, bufs, stream));
+    for (;;) {
+        bool stopped = false;
+        BAND_TRY(frame_run(b, &stopped));
+        if (!stopped) return SVGF_OK;
+        BAND_TRY(frame_exchange(b));
+    }
+}
+
+svgf_status svgf_band_create_group(svgf_band **out, const int32_t *devices, int world, int width, int full_height, svgf_storage storage,
+                                   const int32_t *row_bounds) {
+    if (!out || !devices || world < 1) return SVGF_INVALID_ARG;
+    for (int g = 0; g < world; g++) out[g] = nullptr;
+    for (int g = 0; g < world; g++) {
+        const svgf_status st = band_create(&out[g], devices[g], g, world, width, full_height, storage, nullptr, row_bounds, true);
+        if (st != SVGF_OK) {
+            for (int k = 0; k < g; k++) { svgf_band_destroy(out[k]); out[k] = nullptr; }
+            return st;
+        }
+    }
+    for (int g = 0; g < world; g++) {
+        out[g]->up = g > 0 ? out[g - 1] : nullptr;
+        out[g]->down = g + 1 < world ? out[g + 1] : nullptr;
+    }
+    return SVGF_OK;
+}
+
+svgf_status svgf_band_group_frame(svgf_band *const *bands, int world, const svgf_params *params, const svgf_gbuffer *gbufs,
+                                  const svgf_frame_buffers *bufs, void *const *streams) {
+    if (!bands || !params || !gbufs || !bufs || !streams || world < 1) return SVGF_INVALID_ARG;
+    for (int g = 0; g < world; g++)
+        if (!bands[g] || !bands[g]->in_group || bands[g]->world != world || bands[g]->rank != g) return SVGF_INVALID_ARG;
+    if (world == 1) return svgf_frame(bands[0]->ctx, params, gbufs, bufs, streams[0]);
+    // every band up to its next exchange, then every band's exchange (each waits for its neighbours' `ready` events, which
+    // by then have all been recorded), and so on: all bands stop at the same exchanges in the same order
+    for (int g = 0; g < world; g++) {
+        DeviceScope dev;
+        BAND_TRY(band_cuda(bands[g], dev.enter(bands[g]->device)));
+        BAND_TRY(frame_begin(bands[g], params, gbufs + 2 * g, bufs + g, streams[g]));
+    }
+    for (;;) {
+        int n_stopped = 0;
+        for (int g = 0; g < world; g++) {
+            DeviceScope dev;
+            BAND_TRY(band_cuda(bands[g], dev.enter(bands[g]->device)));
+            bool stopped = false;
+            BAND_TRY(frame_run(bands[g], &stopped));
+            n_stopped += stopped ? 1 : 0;
+        }
+        if (n_stopped == 0) return SVGF_OK;
+        if (n_stopped != world) return SVGF_UNSUPPORTED;                       // cannot happen: the plans exchange alike
+        for (int g = 0; g < world; g++) {
+            DeviceScope dev;
+            BAND_TRY(band_cuda(bands[g], dev.enter(bands[g]->device)));
+            BAND_TRY(frame_exchange(bands[g]));
+        }
+    }
 }
 
 }  // extern "C"
