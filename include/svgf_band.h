@@ -68,6 +68,20 @@ svgf_status svgf_band_create_group(svgf_band **out, const int32_t *devices, int 
 svgf_status svgf_band_group_frame(svgf_band *const *bands, int world, const svgf_params *params, const svgf_gbuffer *gbufs,
                                   const svgf_frame_buffers *bufs, void *const *streams);
 
+/* One process per GPU WITHOUT NCCL: the peer-memory transport.  Every rank exports its exchange planes and a few flag words
+ * as CUDA IPC handles (svgf_band_ipc_export: SVGF_BAND_IPC_BYTES opaque bytes, to be handed to the two neighbouring ranks by
+ * any means - torch.distributed.all_gather_object, MPI, a file) and maps its neighbours' (svgf_band_ipc_connect: the blob of
+ * rank - 1 and of rank + 1, NULL where there is none).  svgf_band_frame then exchanges with ONE kernel per exchange on the
+ * side stream: it waits for the neighbours' "rows ready" flags, pulls their rows over NVLink (peer loads) into the local
+ * aprons and acknowledges, so that a producer never overwrites rows a slower neighbour has not fetched.  Same plan, same
+ * kernels and bit-identical results as the NCCL transport; no SM-resident proxy, no host involvement per exchange.  A
+ * neighbour that never arrives turns into a CUDA error after ~10 s (the wait traps), not a hang. */
+#define SVGF_BAND_IPC_BYTES 640
+svgf_status svgf_band_create_ipc(svgf_band **out, int device, int rank, int world, int width, int full_height, svgf_storage storage,
+                                 const int32_t *row_bounds);
+svgf_status svgf_band_ipc_export(svgf_band *b, void *blob_out);
+svgf_status svgf_band_ipc_connect(svgf_band *b, const void *up_blob, const void *down_blob);
+
 /* Makes `stream` wait for every exchange this driver has posted (before reading state planes from outside). */
 svgf_status svgf_band_sync(svgf_band *b, void *stream);
 

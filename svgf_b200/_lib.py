@@ -107,6 +107,9 @@ ABI += [
     ("svgf_band_frame", C.c_int, [C.c_void_p, C.POINTER(SvgfParams), C.POINTER(SvgfGBuffer * 2), C.POINTER(SvgfFrameBuffers),
                                   C.c_void_p]),
     ("svgf_band_sync", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("svgf_band_create_ipc", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
+    ("svgf_band_ipc_export", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("svgf_band_ipc_connect", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     ("svgf_band_create_group", C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(C.c_int32)]),
     ("svgf_band_group_frame", C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(SvgfParams), C.POINTER(SvgfGBuffer),

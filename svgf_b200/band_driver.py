@@ -33,12 +33,31 @@ def broadcast_unique_id(rank, src=0, group=None, device=None):
 
 class BandDriver:
     def __init__(self, width, height, rank, world, device, storage="f16", levels=5, bounds=None, unique_id=None, group=None,
-                 _handle=None):
+                 _handle=None, transport="nccl"):
+        """transport: "nccl" (send/recv on a driver-owned communicator) or "ipc" (peer-memory pulls over NVLink: CUDA IPC
+        handles exchanged once through torch.distributed, any backend; no NCCL on the data path)."""
         self.lib = _lib.lib()
         self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
         self.rank, self.world, self.Width, self.FullHeight = rank, world, int(width), int(height)
+        self.transport = transport
         if _handle is not None:                                # a member of a BandGroup: the group created the native band
             self._h = _handle
+        elif transport == "ipc":
+            import torch.distributed as dist
+            rb = (C.c_int32 * (world + 1))(*bounds) if bounds is not None else None
+            self._h = C.c_void_p()
+            st = self.lib.svgf_band_create_ipc(C.byref(self._h), self.device.index or 0, rank, world, self.Width, self.FullHeight,
+                                               {"f16": _lib.SVGF_STORE_F16, "f32": _lib.SVGF_STORE_F32}[storage], rb)
+            if st != _lib.SVGF_OK:
+                raise SvgfError(st, "svgf_band_create_ipc")
+            if world > 1:
+                blob = (C.c_ubyte * 640)()
+                self._check(self.lib.svgf_band_ipc_export(self._h, blob), "svgf_band_ipc_export")
+                blobs = [None] * world
+                dist.all_gather_object(blobs, bytes(blob), group=group)
+                up = (C.c_ubyte * 640)(*blobs[rank - 1]) if rank > 0 else None
+                down = (C.c_ubyte * 640)(*blobs[rank + 1]) if rank + 1 < world else None
+                self._check(self.lib.svgf_band_ipc_connect(self._h, up, down), "svgf_band_ipc_connect")
         else:
             if world > 1 and unique_id is None:
                 unique_id = broadcast_unique_id(rank, group=group, device=self.device)

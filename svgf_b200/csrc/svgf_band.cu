@@ -68,6 +68,95 @@ struct Plane {          // rows of a local image as one contiguous run per row r
 };
 struct PlaneSet { const Plane *planes; int n; int rows; };
 
+// ---- the peer-memory transport (svgf_band_create_ipc): flags and pulls over NVLink, no NCCL ---------------------------------
+// Every rank exports its lattice colour planes, a staging block for the state rows and a few flag words (cudaIpc handles);
+// a neighbour maps them.  An exchange is ONE kernel on the consumer's side stream: wait for the producers' READY flags,
+// copy their rows over NVLink into the local aprons, tell them the rows have been read (PULLED flags, so that a producer
+// never overwrites rows a slower neighbour has not fetched yet).  Flags are monotonically increasing sequence numbers.
+struct PullJob { const char *src; char *dst; unsigned long long bytes; };
+struct FlagRef { unsigned *p; unsigned v; };
+struct PullArgs {
+    PullJob job[12];
+    FlagRef wait[4], signal[4];
+    unsigned *counter;
+    int njobs, nwait, nsignal;
+};
+struct FlagArgs { FlagRef wait[4], set[4]; int nwait, nset; };
+
+constexpr long long kSpinLimitClocks = 20000000000LL;      // ~10 s: a neighbour that never arrives becomes a CUDA error, not a hang
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ void spin_until_reached(const unsigned *p, unsigned v) {
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(p) - v) < 0) {
+        __nanosleep(100);
+        if (clock64() - t0 > kSpinLimitClocks) __trap();
+    }
+}
+
+__global__ void __launch_bounds__(256) band_pull_kernel(PullArgs a) {
+    if (threadIdx.x == 0)
+        for (int i = 0; i < a.nwait; i++) spin_until_reached(a.wait[i].p, a.wait[i].v);
+    __syncthreads();
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (int j = 0; j < a.njobs; j++) {
+        const PullJob q = a.job[j];
+        if (((reinterpret_cast<size_t>(q.src) | reinterpret_cast<size_t>(q.dst) | q.bytes) & 15) == 0) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(q.src);
+            uint4 *dst = reinterpret_cast<uint4 *>(q.dst);
+            const size_t n = q.bytes >> 4;
+            size_t k = tid;
+            for (; k + 3 * nth < n; k += 4 * nth) {        // four loads in flight per thread: the round trip is an NVLink hop
+                const uint4 v0 = __ldcv(src + k), v1 = __ldcv(src + k + nth), v2 = __ldcv(src + k + 2 * nth), v3 = __ldcv(src + k + 3 * nth);
+                dst[k] = v0; dst[k + nth] = v1; dst[k + 2 * nth] = v2; dst[k + 3 * nth] = v3;
+            }
+            for (; k < n; k += nth) dst[k] = __ldcv(src + k);
+        } else {                                            // history lengths of a width that is not a multiple of 16
+            for (size_t k = tid; k < q.bytes; k += nth) q.dst[k] = __ldcv(q.src + k);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.counter, 1u) == gridDim.x - 1) {    // last CTA: every row has been read
+            *a.counter = 0;
+            __threadfence_system();
+            for (int i = 0; i < a.nsignal; i++) st_release_sys(a.signal[i].p, a.signal[i].v);
+        }
+    }
+}
+
+__global__ void band_flag_kernel(FlagArgs a) {
+    for (int i = 0; i < a.nwait; i++) spin_until_reached(a.wait[i].p, a.wait[i].v);
+    __threadfence_system();
+    for (int i = 0; i < a.nset; i++) st_release_sys(a.set[i].p, a.set[i].v);
+}
+
+struct IpcBlob {                       // what svgf_band_ipc_export hands to the neighbours (SVGF_BAND_IPC_BYTES)
+    unsigned magic;
+    int width, storage, band_lo, band_hi, local_rows, pitch_pairs;
+    cudaIpcMemHandle_t planes[6], staging, flags;
+};
+constexpr unsigned kIpcMagic = 0x53424950u;   // "SBIP"
+static_assert(sizeof(IpcBlob) <= SVGF_BAND_IPC_BYTES, "IpcBlob must fit the public blob size");
+
+struct IpcPeer {
+    bool open = false;
+    char *planes[6] = {};              // lattice colour planes sc[0].{c0,c1,lz}, sc[1].{c0,c1,lz}
+    char *staging = nullptr;
+    unsigned *flags = nullptr;
+    int band_lo = 0, band_hi = 0;
+};
+// flag words (each rank owns one array; 32 words apart so that two never share a line)
+enum { kFlagReadyHalo = 0, kFlagReadyState = 1, kFlagPulledHalo = 2 /* +dir */, kFlagPulledState = 4 /* +dir */, kFlagWords = 6, kFlagStride = 32 };
+
 }  // namespace
 
 struct svgf_band {
@@ -83,6 +172,14 @@ struct svgf_band {
     // in-process group (svgf_band_create_group): the neighbours' bands; halos are copied from their planes
     bool in_group = false;
     svgf_band *up = nullptr, *down = nullptr;
+    // peer-memory transport (svgf_band_create_ipc)
+    bool ipc = false, ipc_connected = false;
+    IpcPeer peer[2];                   // 0 = up (rank - 1), 1 = down (rank + 1)
+    char *staging = nullptr;           // [side 0 = my top band rows, 1 = bottom][colour, moments, history] of the last frame
+    size_t staging_side_bytes = 0;
+    unsigned *flags = nullptr, *pull_counter = nullptr;
+    unsigned ticket = 0, halo_seq = 0; // frames begun / halo exchanges posted (the same on every rank)
+    uint64_t extra_launches = 0;       // flag and pull kernels (svgf_band_launch_count)
 
     // ---- the frame in flight: svgf_band_frame / svgf_band_group_frame advance it from exchange to exchange ----
     struct Frame {
@@ -123,6 +220,16 @@ svgf_status band_nccl(svgf_band *b, int r) {
         const svgf_status st_ = (x);      \
         if (st_ != SVGF_OK) return st_;   \
     } while (0)
+
+struct DeviceScope {
+    int prev = -1, cur = -1;
+    cudaError_t enter(int device) {
+        cudaGetDevice(&prev);
+        cur = device;
+        return prev != device ? cudaSetDevice(device) : cudaSuccess;
+    }
+    ~DeviceScope() { if (prev >= 0 && prev != cur) cudaSetDevice(prev); }
+};
 
 // Refresh the apron rows on each side of the band with the neighbours' band rows, for every plane of up to two plane sets
 // (each with its own row count): ONE grouped send/recv on the side stream.
@@ -171,6 +278,97 @@ svgf_status exchange_copy(svgf_band *b) {
             }
         }
     return SVGF_OK;
+}
+
+svgf_status launch_flags(svgf_band *b, const FlagArgs &a, cudaStream_t s) {
+    band_flag_kernel<<<1, 1, 0, s>>>(a);
+    b->extra_launches++;
+    return band_cuda(b, cudaGetLastError());
+}
+
+// Peer-memory transport, frame begin (main stream): the rows this frame is about to overwrite - boundary rows of the lattice
+// planes, the state staging block - must have been fetched by the neighbours (they were, long ago, unless a rank lags).
+svgf_status ipc_wait_pulled(svgf_band *b, cudaStream_t s) {
+    FlagArgs a{};
+    for (int d = 0; d < 2; d++) {
+        if (!b->peer[d].open) continue;
+        a.wait[a.nwait++] = FlagRef{b->flags + (kFlagPulledHalo + d) * kFlagStride, b->halo_seq};
+        a.wait[a.nwait++] = FlagRef{b->flags + (kFlagPulledState + d) * kFlagStride, b->ticket - 1};
+    }
+    return launch_flags(b, a, s);
+}
+
+// Peer-memory transport, after level 0 (side stream): this frame's state rows next to each neighbour -> staging, READY_STATE.
+svgf_status ipc_publish_state(svgf_band *b) {
+    const svgf_band::Frame &f = b->f;
+    const int lo = b->band_lo(), hi = b->band_hi();
+    for (int d = 0; d < 2; d++) {
+        if (!b->peer[d].open) continue;
+        char *dst = b->staging + (size_t)d * b->staging_side_bytes;
+        const int row0 = d == 0 ? lo : hi - SVGF_BAND_APRON;
+        for (int k = 0; k < 3; k++) {
+            const size_t bytes = (size_t)SVGF_BAND_APRON * f.state[k].row_bytes;
+            BAND_TRY(band_cuda(b, cudaMemcpyAsync(dst, f.state[k].base + (size_t)row0 * f.state[k].row_bytes, bytes, cudaMemcpyDeviceToDevice, b->side)));
+            dst += bytes;
+        }
+    }
+    FlagArgs a{};
+    a.set[a.nset++] = FlagRef{b->flags + kFlagReadyState * kFlagStride, b->ticket};
+    return launch_flags(b, a, b->side);
+}
+
+// Peer-memory transport, one exchange (side stream, after the event that says this band's rows are final): READY_HALO for
+// the neighbours, then ONE kernel that waits for theirs, pulls their rows into the aprons and acknowledges.
+svgf_status exchange_ipc(svgf_band *b) {
+    if (b->dry_run) return SVGF_OK;
+    svgf_band::Frame &f = b->f;
+    const bool has_halo = f.pc >= 0;
+    const int lo = b->band_lo(), hi = b->band_hi();
+    if (has_halo) {
+        b->halo_seq++;
+        FlagArgs r{};
+        r.set[r.nset++] = FlagRef{b->flags + kFlagReadyHalo * kFlagStride, b->halo_seq};
+        BAND_TRY(launch_flags(b, r, b->side));
+    }
+    PullArgs a{};
+    a.counter = b->pull_counter;
+    unsigned long long total = 0;
+    const size_t pad = has_halo ? (size_t)svgf::kLatPadY * f.lattice[0].row_bytes : 0;
+    const int set_base = (1 - f.src) * 3;                  // the lattice colour set this level wrote, here and on the neighbours
+    for (int d = 0; d < 2; d++) {
+        const IpcPeer &p = b->peer[d];
+        if (!p.open) continue;
+        const int mine_at_peer = 1 - d;                    // the upper neighbour knows this band as its `down`
+        if (has_halo) {
+            const int rows = f.sets[0].rows;
+            a.wait[a.nwait++] = FlagRef{p.flags + kFlagReadyHalo * kFlagStride, b->halo_seq};
+            a.signal[a.nsignal++] = FlagRef{p.flags + (kFlagPulledHalo + mine_at_peer) * kFlagStride, b->halo_seq};
+            for (int k = 0; k < 3; k++) {
+                const size_t rb = f.lattice[k].row_bytes, bytes = (size_t)rows * rb;
+                const char *src = p.planes[set_base + k] + pad + (size_t)(d == 0 ? p.band_hi - rows : p.band_lo) * rb;
+                char *dst = f.lattice[k].base + (size_t)(d == 0 ? lo - rows : hi) * rb;
+                a.job[a.njobs++] = PullJob{src, dst, bytes};
+                total += bytes;
+            }
+        }
+        if (f.carries_state) {
+            a.wait[a.nwait++] = FlagRef{p.flags + kFlagReadyState * kFlagStride, b->ticket};
+            a.signal[a.nsignal++] = FlagRef{p.flags + (kFlagPulledState + mine_at_peer) * kFlagStride, b->ticket};
+            const char *src = p.staging + (size_t)mine_at_peer * b->staging_side_bytes;   // the upper neighbour's BOTTOM rows, the lower one's TOP rows
+            for (int k = 0; k < 3; k++) {
+                const size_t rb = f.state[k].row_bytes, bytes = (size_t)SVGF_BAND_APRON * rb;
+                char *dst = f.state[k].base + (size_t)(d == 0 ? lo - SVGF_BAND_APRON : hi) * rb;
+                a.job[a.njobs++] = PullJob{src, dst, bytes};
+                src += bytes;
+                total += bytes;
+            }
+        }
+    }
+    int grid = (int)(total / (256ull * 16 * 8)) + 1;
+    if (grid > 64) grid = 64;
+    band_pull_kernel<<<grid, 256, 0, b->side>>>(a);
+    b->extra_launches++;
+    return band_cuda(b, cudaGetLastError());
 }
 
 }  // namespace
@@ -233,10 +431,13 @@ svgf_status svgf_band_unique_id(void *id_out) {
     return SVGF_OK;
 }
 
+enum BandTransport { kTransportNccl = 0, kTransportGroup = 1, kTransportIpc = 2 };
+
 static svgf_status band_create(svgf_band **out, int device, int rank, int world, int width, int full_height, svgf_storage storage,
-                               const void *unique_id, const int32_t *row_bounds, bool in_group) {
+                               const void *unique_id, const int32_t *row_bounds, int transport) {
+    const bool in_group = transport == kTransportGroup, use_nccl = transport == kTransportNccl;
     if (!out || world < 1 || rank < 0 || rank >= world || width <= 0 || full_height <= 0) return SVGF_INVALID_ARG;
-    if (world > 1 && !unique_id && !in_group) return SVGF_INVALID_ARG;
+    if (world > 1 && !unique_id && use_nccl) return SVGF_INVALID_ARG;
     *out = nullptr;
     int y0, y1;
     if (row_bounds) {
@@ -253,11 +454,12 @@ static svgf_status band_create(svgf_band **out, int device, int rank, int world,
         y1 = y0 + base + (rank < rem ? 1 : 0);
         if (world > 1 && base < SVGF_BAND_APRON) return SVGF_UNSUPPORTED;
     }
-    if (world > 1 && !in_group && !nccl().ok) return SVGF_UNSUPPORTED;
+    if (world > 1 && use_nccl && !nccl().ok) return SVGF_UNSUPPORTED;
     svgf_band *b = new (std::nothrow) svgf_band();
     if (!b) return SVGF_CUDA_ERROR;
     b->device = device; b->rank = rank; b->world = world; b->W = width; b->H = full_height;
     b->in_group = in_group;
+    b->ipc = transport == kTransportIpc;
     b->y0 = y0; b->y1 = y1;
     b->ly0 = (world > 1 && y0 - SVGF_BAND_APRON > 0) ? y0 - SVGF_BAND_APRON : (world > 1 ? 0 : y0);
     b->ly1 = (world > 1 && y1 + SVGF_BAND_APRON < full_height) ? y1 + SVGF_BAND_APRON : (world > 1 ? full_height : y1);
@@ -277,7 +479,18 @@ static svgf_status band_create(svgf_band **out, int device, int rank, int world,
     for (cudaEvent_t *ev : evs)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     int nr = 0;
-    if (e == cudaSuccess && world > 1 && !in_group) {
+    if (e == cudaSuccess && world > 1 && b->ipc) {
+        // exported memory: plain cudaMalloc (cudaIpcGetMemHandle does not take pooled or virtual-memory allocations)
+        const size_t ct = storage == SVGF_STORE_F32 ? 16 : 8, mt = storage == SVGF_STORE_F32 ? 8 : 4;
+        b->staging_side_bytes = ((size_t)SVGF_BAND_APRON * width * (ct + mt + 1) + 255) & ~(size_t)255;
+        e = cudaMalloc(&b->staging, 2 * b->staging_side_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&b->flags, (kFlagWords * kFlagStride + 1) * sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMemset(b->flags, 0, (kFlagWords * kFlagStride + 1) * sizeof(unsigned));
+        if (e == cudaSuccess) b->pull_counter = b->flags + kFlagWords * kFlagStride;
+        if (e == cudaSuccess && svgf::lattice_prepare(b->ctx, nullptr) != SVGF_OK) e = cudaErrorMemoryAllocation;
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    }
+    if (e == cudaSuccess && world > 1 && use_nccl) {
         NcclUniqueId id;
         std::memcpy(&id, unique_id, sizeof(id));
         nr = nccl().CommInitRank(&b->comm, world, id, rank);
@@ -290,7 +503,56 @@ static svgf_status band_create(svgf_band **out, int device, int rank, int world,
 
 svgf_status svgf_band_create(svgf_band **out, int device, int rank, int world, int width, int full_height, svgf_storage storage,
                              const void *unique_id, const int32_t *row_bounds) {
-    return band_create(out, device, rank, world, width, full_height, storage, unique_id, row_bounds, false);
+    return band_create(out, device, rank, world, width, full_height, storage, unique_id, row_bounds, kTransportNccl);
+}
+
+svgf_status svgf_band_create_ipc(svgf_band **out, int device, int rank, int world, int width, int full_height, svgf_storage storage,
+                                 const int32_t *row_bounds) {
+    return band_create(out, device, rank, world, width, full_height, storage, nullptr, row_bounds, kTransportIpc);
+}
+
+svgf_status svgf_band_ipc_export(svgf_band *b, void *blob_out) {
+    if (!b || !blob_out || !b->ipc) return SVGF_INVALID_ARG;
+    IpcBlob blob;
+    std::memset(&blob, 0, sizeof(blob));
+    if (b->world > 1) {
+        const svgf_ctx *c = b->ctx;
+        blob.magic = kIpcMagic; blob.width = b->W; blob.storage = (int)c->storage;
+        blob.band_lo = b->band_lo(); blob.band_hi = b->band_hi(); blob.local_rows = b->local_rows(); blob.pitch_pairs = c->lat.pitch_pairs;
+        DeviceScope dev;
+        BAND_TRY(band_cuda(b, dev.enter(b->device)));
+        void *planes[6] = {c->lat.sc[0].c0, c->lat.sc[0].c1, c->lat.sc[0].lz, c->lat.sc[1].c0, c->lat.sc[1].c1, c->lat.sc[1].lz};
+        for (int k = 0; k < 6; k++) BAND_TRY(band_cuda(b, cudaIpcGetMemHandle(&blob.planes[k], planes[k])));
+        BAND_TRY(band_cuda(b, cudaIpcGetMemHandle(&blob.staging, b->staging)));
+        BAND_TRY(band_cuda(b, cudaIpcGetMemHandle(&blob.flags, b->flags)));
+    }
+    std::memset(blob_out, 0, SVGF_BAND_IPC_BYTES);
+    std::memcpy(blob_out, &blob, sizeof(blob));
+    return SVGF_OK;
+}
+
+svgf_status svgf_band_ipc_connect(svgf_band *b, const void *up_blob, const void *down_blob) {
+    if (!b || !b->ipc || b->ipc_connected) return SVGF_INVALID_ARG;
+    if ((b->rank > 0) != (up_blob != nullptr) || (b->rank + 1 < b->world) != (down_blob != nullptr)) return SVGF_INVALID_ARG;
+    DeviceScope dev;
+    BAND_TRY(band_cuda(b, dev.enter(b->device)));
+    const void *blobs[2] = {up_blob, down_blob};
+    for (int d = 0; d < 2; d++) {
+        if (!blobs[d]) continue;
+        IpcBlob blob;
+        std::memcpy(&blob, blobs[d], sizeof(blob));
+        if (blob.magic != kIpcMagic || blob.width != b->W || blob.storage != (int)b->ctx->storage || blob.pitch_pairs != b->ctx->lat.pitch_pairs)
+            return SVGF_INVALID_ARG;
+        IpcPeer &p = b->peer[d];
+        p.band_lo = blob.band_lo; p.band_hi = blob.band_hi;
+        for (int k = 0; k < 6; k++)
+            BAND_TRY(band_cuda(b, cudaIpcOpenMemHandle((void **)&p.planes[k], blob.planes[k], cudaIpcMemLazyEnablePeerAccess)));
+        BAND_TRY(band_cuda(b, cudaIpcOpenMemHandle((void **)&p.staging, blob.staging, cudaIpcMemLazyEnablePeerAccess)));
+        BAND_TRY(band_cuda(b, cudaIpcOpenMemHandle((void **)&p.flags, blob.flags, cudaIpcMemLazyEnablePeerAccess)));
+        p.open = true;
+    }
+    b->ipc_connected = true;
+    return SVGF_OK;
 }
 
 void svgf_band_destroy(svgf_band *b) {
@@ -302,6 +564,14 @@ void svgf_band_destroy(svgf_band *b) {
     if (b->up) { cudaStreamSynchronize(b->up->side); b->up->down = nullptr; }       // a neighbour's copies read this band's planes
     if (b->down) { cudaStreamSynchronize(b->down->side); b->down->up = nullptr; }
     if (b->comm) nccl().CommDestroy(b->comm);
+    for (IpcPeer &p : b->peer) {
+        for (char *q : p.planes)
+            if (q) cudaIpcCloseMemHandle(q);
+        if (p.staging) cudaIpcCloseMemHandle(p.staging);
+        if (p.flags) cudaIpcCloseMemHandle(p.flags);
+    }
+    if (b->staging) cudaFree(b->staging);
+    if (b->flags) cudaFree(b->flags);
     if (b->side) cudaStreamDestroy(b->side);
     cudaEvent_t evs[] = {b->ev_l0, b->ev_boundary[0], b->ev_boundary[1], b->ev_halo[0], b->ev_halo[1], b->ev_state};
     for (cudaEvent_t ev : evs)
@@ -316,7 +586,7 @@ void svgf_band_rows(const svgf_band *b, int32_t rows[4]) {
     rows[0] = b->y0; rows[1] = b->y1; rows[2] = b->ly0; rows[3] = b->ly1;
 }
 
-uint64_t svgf_band_launch_count(const svgf_band *b) { return b ? svgf_launch_count(b->ctx) : 0; }
+uint64_t svgf_band_launch_count(const svgf_band *b) { return b ? svgf_launch_count(b->ctx) + b->extra_launches : 0; }
 int svgf_band_last_error(const svgf_band *b) { return !b ? 0 : (b->last_err ? b->last_err : svgf_last_cuda_error(b->ctx)); }
 
 svgf_status svgf_band_sync(svgf_band *b, void *stream) {
@@ -350,6 +620,11 @@ svgf_status frame_begin(svgf_band *b, const svgf_params *params, const svgf_gbuf
 
     // previous-frame state in the aprons: posted under the previous frame's levels
     BAND_TRY(svgf_band_sync(b, stream));
+    if (b->ipc) {
+        if (!b->ipc_connected) return SVGF_INVALID_ARG;
+        b->ticket++;
+        if (!b->dry_run) BAND_TRY(ipc_wait_pulled(b, s));
+    }
     if (b->in_group) {
         // a neighbour copies rows out of THIS band's planes on its own side stream: this frame must not overwrite them
         // before those copies (all posted during the previous group frame) have run
@@ -379,6 +654,10 @@ svgf_status frame_begin(svgf_band *b, const svgf_params *params, const svgf_gbuf
     f.state[0] = Plane{(char *)bufs->render[P], (size_t)b->W * ct};
     f.state[1] = Plane{(char *)bufs->moments[P], (size_t)b->W * mt};
     f.state[2] = Plane{(char *)bufs->history, (size_t)b->W};
+    if (b->ipc && !b->dry_run) {
+        BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, b->ev_l0, 0)));
+        BAND_TRY(ipc_publish_state(b));
+    }
 
     // levels 1..N-1 as planned by svgf_band_plan (the same function the CPU tests check)
     f.n_steps = svgf_band_plan(b->rank, b->world, b->band_lo(), b->band_hi(), b->local_rows(), N, f.steps, 32);
@@ -442,6 +721,8 @@ svgf_status frame_exchange(svgf_band *b) {
         for (svgf_band *nb : {b->up, b->down})
             if (nb) BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, nb->f.ready, 0)));
         BAND_TRY(exchange_copy(b));
+    } else if (b->ipc) {
+        BAND_TRY(exchange_ipc(b));
     } else {
         BAND_TRY(exchange(b, f.sets, f.n_sets));
     }
@@ -454,16 +735,6 @@ svgf_status frame_exchange(svgf_band *b) {
     f.pc++;                                        // -1 -> 0: the steps follow the state-only exchange
     return SVGF_OK;
 }
-
-struct DeviceScope {
-    int prev = -1, cur = -1;
-    cudaError_t enter(int device) {
-        cudaGetDevice(&prev);
-        cur = device;
-        return prev != device ? cudaSetDevice(device) : cudaSuccess;
-    }
-    ~DeviceScope() { if (prev >= 0 && prev != cur) cudaSetDevice(prev); }
-};
 
 }  // namespace
 
@@ -488,7 +759,7 @@ svgf_status svgf_band_create_group(svgf_band **out, const int32_t *devices, int 
     if (!out || !devices || world < 1) return SVGF_INVALID_ARG;
     for (int g = 0; g < world; g++) out[g] = nullptr;
     for (int g = 0; g < world; g++) {
-        const svgf_status st = band_create(&out[g], devices[g], g, world, width, full_height, storage, nullptr, row_bounds, true);
+        const svgf_status st = band_create(&out[g], devices[g], g, world, width, full_height, storage, nullptr, row_bounds, kTransportGroup);
         if (st != SVGF_OK) {
             for (int k = 0; k < g; k++) { svgf_band_destroy(out[k]); out[k] = nullptr; }
             return st;
