@@ -376,8 +376,10 @@ def run_streams_1080p(args, rank, world, local):
             "ms_total": round(ms_max, 3), "streams_per_gpu": len(mine), "gpu_launches": int(launches), "scaling": "strong (64 streams in total)"}
 
 
-def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames):
-    """K timed 8K frames in `world` bands through the native band driver + a bit-identity check on rank 0."""
+def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames, transport=None, fixed_bounds=None):
+    """K timed 8K frames in `world` bands through the native band driver + a bit-identity check on rank 0.
+    transport: "ipc" (peer-memory pulls over NVLink) or "nccl" (send/recv); fixed_bounds: skip the balancing passes."""
+    transport = transport or args.band_transport
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -388,18 +390,18 @@ def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames):
     dev = torch.device("cuda", local)
     cdt = torch.float16 if args.storage == "f16" else torch.float32
     full_g, full_c = GBuffer(W, H, dev), torch.empty(H, W, 4, dtype=cdt, device=dev)
-    bounds = None
-    if args.band_balance and world > 1:
+    bounds = fixed_bounds
+    if args.band_balance and world > 1 and fixed_bounds is None:
         # equal estimated work per band: background pixels (linear depth 0) are passed through by the a-trous levels
         synth.frame_device(full_g, full_c, 0, seed=0)
         live = (full_g.motion[..., 2] != 0).float().mean(dim=1).cpu().numpy()
         bounds = balanced_bounds(live + args.band_bg_cost * (1.0 - live), world, min_rows=32)
     def make_driver(bnds):
         with stdout_to_stderr():
-            return BandDriver(W, H, rank, world, dev, storage=args.storage, levels=args.levels, bounds=bnds)
+            return BandDriver(W, H, rank, world, dev, storage=args.storage, levels=args.levels, bounds=bnds, transport=transport)
 
     calibration = []
-    if args.band_balance >= 2 and world > 1:
+    if args.band_balance >= 2 and world > 1 and fixed_bounds is None:
         # measured balance: a few frames WITHOUT exchanges (SVGF_FLAG_BAND_NO_EXCHANGE: every rank runs at its own speed)
         # give each band's cost per row; the boundaries are moved to equalise the predicted times.  Twice.
         for it in range(2):
@@ -527,7 +529,9 @@ def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames):
     frame_bytes = (bpp["temporal"] + bpp["variance"] + bpp["atrous_level"] * args.levels + (bpp["atrous_hist"] if args.levels else 0)) * W * H
     peak, _ = measured_peaks()
     return {"workload": f"BASELINE configs[3]: {W}x{H} frames in {world} horizontal band(s), native band driver (include/svgf_band.h): "
-                        "NCCL send/recv of 16 + 32 halo rows before levels 3 and 4, boundary row blocks first, state exchange under levels 1-4",
+                        + ("peer-memory transport (CUDA IPC mappings, flag words, one pull kernel per exchange over NVLink)" if transport == "ipc" else "NCCL send/recv")
+                        + " of 16 + 32 halo rows before levels 3 and 4, boundary row blocks first, state exchange under levels 1-4",
+            "transport": transport,
             "value": round(value, 4), "unit": "Gpix/s", "ms_per_step": round(ms_max / K, 5), "steps": K, "warmup": Wm, "scaling": "strong",
             "band_bounds": bounds, "band_balance": {0: "equal heights", 1: "background share of the first frame", 2: "measured: two calibration passes without exchanges"}[min(args.band_balance, 2)],
             "calibration_ms_by_rank": calibration or None, "local_rows_by_rank": rows, "ms_per_step_by_rank": [round(v, 4) for v in ms_by_rank],
@@ -670,6 +674,10 @@ def run_ours(args, rank, world, local):
         if world > 1:
             bw, bh = WORKLOADS["8k"]
             bands_rec = run_band_frames(args, rank, world, local, bw, bh, K=args.band_frames, Wm=4, check_frames=3)
+            # the same frames, same band heights, over the other transport (timing only)
+            other = "nccl" if args.band_transport == "ipc" else "ipc"
+            bands_other = run_band_frames(args, rank, world, local, bw, bh, K=args.band_frames, Wm=4, check_frames=1, transport=other,
+                                          fixed_bounds=bands_rec["band_bounds"])
 
     if rank != 0:
         return None
@@ -716,6 +724,8 @@ def run_ours(args, rank, world, local):
         line["streams_1080p"] = streams_rec
     if bands_rec:
         line["bands"] = bands_rec
+        line["bands_" + bands_other["transport"]] = {k: bands_other[k] for k in ("transport", "value", "unit", "ms_per_step", "steps", "ms_per_step_by_rank",
+                                                                                   "bit_identical_to_one_gpu", "checked_frames", "gpu_launches")}
     return line
 
 
@@ -728,7 +738,7 @@ def run_bands(args, rank, world, local):
         return None
     cfg = base_config(W, H, args.levels, args.storage)
     cfg["workload"] = rec.pop("workload")
-    for k in ("band_bounds", "band_balance", "calibration_ms_by_rank", "local_rows_by_rank", "ms_per_step_by_rank", "bit_identical_to_one_gpu", "checked_frames", "mismatching_bytes"):
+    for k in ("transport", "band_bounds", "band_balance", "calibration_ms_by_rank", "local_rows_by_rank", "ms_per_step_by_rank", "bit_identical_to_one_gpu", "checked_frames", "mismatching_bytes"):
         cfg[k] = rec.pop(k)
     return {"metric": "svgf_frame_throughput", "value": rec["value"], "unit": "Gpix/s", "n_gpus": world, "steps": rec["steps"], "warmup": rec["warmup"],
             "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -906,6 +916,7 @@ def main():
     ap.add_argument("--prefilter", type=int, default=0, help="svgf_params.variance_prefilter (1 = 3x3 Gaussian, not in the reference)")
     ap.add_argument("--reproj", type=int, default=0, help="svgf_params.reproj_mode (1 = bilinear 2x2, not in the reference)")
     ap.add_argument("--flags", type=int, default=0, help="svgf_params.flags for A/B runs (8 = no uniform-normal tile shortcut, 32 = no staged levels)")
+    ap.add_argument("--band-transport", default="ipc", choices=["ipc", "nccl"], help="bands: halo transport of the native driver")
     ap.add_argument("--band-balance", type=int, default=2, help="bands: 0 = equal heights, 1 = heights balanced by the background share of the first frame, 2 = 1 + two measured calibration passes")
     ap.add_argument("--band-bg-cost", type=float, default=0.45, help="bands: cost of a background pixel relative to a filtered one")
     ap.add_argument("--mode", default="streams", choices=["streams", "bands"],

@@ -92,20 +92,36 @@ def test_band_plan_rejects_what_the_driver_does_not_do():
     assert lib.svgf_band_plan(0, 2, 0, 500, 532, 5, steps, 2) == -1       # list too short
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("size,levels,storage", [((1920, 1080), 5, "f16"), ((1030, 420), 5, "f32"), ((1280, 720), 4, "f16"),
-                                                 ((1280, 720), 3, "f16"), ((1280, 720), 2, "f16")])
-def test_stitched_bands_equal_the_whole_frame_over_nccl(size, levels, storage):
-    import torch
-    n = min(torch.cuda.device_count(), 4)
-    if n < 2:
-        pytest.skip("needs two or more GPUs (bench.py --gpus N records the same check in its JSON line)")
+def _band_check(n, size, levels, storage, extra, port):
     W, H = size
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-                        "--master-port", "29517", os.path.join(ROOT, "tools", "band_check.py"), "--width", str(W), "--height", str(H),
-                        "--levels", str(levels), "--storage", storage], capture_output=True, text=True, timeout=600)
+                        "--master-port", str(port), os.path.join(ROOT, "tools", "band_check.py"), "--width", str(W), "--height", str(H),
+                        "--levels", str(levels), "--storage", storage] + extra, capture_output=True, text=True, timeout=600)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert lines, r.stdout[-1500:] + r.stderr[-3000:]
     res = json.loads(lines[-1])
     assert res["bit_identical"], res
     assert r.returncode == 0
+    return res
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transport", ["nccl", "ipc"])
+@pytest.mark.parametrize("size,levels,storage", [((1920, 1080), 5, "f16"), ((1030, 420), 5, "f32"), ((1280, 720), 4, "f16"),
+                                                 ((1280, 720), 3, "f16"), ((1280, 720), 2, "f16")])
+def test_stitched_bands_equal_the_whole_frame_over_real_ranks(size, levels, storage, transport):
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs two or more GPUs (bench.py --gpus N records the same check in its JSON line)")
+    _band_check(n, size, levels, storage, ["--transport", transport], 29517)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,size,levels,storage", [(2, (1280, 720), 5, "f16"), (3, (1920, 1080), 5, "f16"), (4, (1030, 420), 5, "f32"),
+                                                   (3, (1280, 720), 3, "f16"), (8, (1920, 1080), 5, "f16")])
+def test_peer_memory_transport_with_every_rank_on_one_gpu(n, size, levels, storage):
+    """n PROCESSES time-slicing cuda:0 (torch.distributed on gloo): real CUDA IPC mappings, real cross-process flag words and
+    pull kernels - the peer-memory transport end to end on a one-GPU box.  Stitched bands == whole frame, bit for bit."""
+    res = _band_check(n, size, levels, storage, ["--transport", "ipc", "--same-gpu", "--frames", "4"], 29519)
+    assert res["transport"] == "ipc" and res["same_gpu"] and res["n_gpus"] == n
