@@ -6,7 +6,9 @@
  * width x (ly1 - ly0); the caller fills the G-buffer and noisy radiance of its local rows (apron included: they are
  * inputs, nobody exchanges them) and reads the result from filter[0], rows [y0 - ly0, y1 - ly0).
  *
- * The path has no all-reduce.  Neighbouring ranks exchange, per frame (NCCL send/recv on a driver-owned side stream):
+ * The path has no all-reduce.  Neighbouring ranks exchange, per frame, on a driver-owned side stream - by NCCL send/recv
+ * (svgf_band_create), by peer-memory pulls over NVLink with one process per GPU and no NCCL (svgf_band_create_ipc), or by
+ * peer copies when one process drives every band (svgf_band_create_group); the schedule and the results are the same:
  *   - before a-trous level 3 the 16 band rows of level 2's output next to each boundary, before level 4 the 32 rows of
  *     level 3's (2 * 2^i rows, reference src/Filter.cuh:571-576).  The level that PRODUCES those rows runs its boundary row
  *     blocks first, the exchange is posted, and the interior row blocks run while the rows are in flight;
@@ -91,7 +93,8 @@ svgf_status svgf_band_sync(svgf_band *b, void *stream);
  *   LAUNCH     level `level` over row blocks [yblock0, yblock0 + nyblocks) of its tile grid (a block = 12 * 2^level rows)
  *              and, when nyblocks1 > 0, [yblock1, yblock1 + nyblocks1) in the same launch (the two boundary strips)
  *   EXCHANGE   post the exchange of `rows` band rows of level `level`'s output with each neighbour (for level + 1)
- *   WAIT_HALO  level `level` is about to start: wait for the exchange of its `rows`-row halo
+ *   WAIT_HALO  wait for the exchange of level `level`'s `rows`-row halo: every later launch of the level may read apron rows
+ *              (launches of the level BEFORE it cover only row blocks further than `rows` rows from a neighbour's edge)
  * Returns the number of steps (<= max_steps), or -1 for unsupported arguments. */
 enum { SVGF_BAND_STEP_LAUNCH = 0, SVGF_BAND_STEP_EXCHANGE = 1, SVGF_BAND_STEP_WAIT_HALO = 2 };
 typedef struct svgf_band_step {

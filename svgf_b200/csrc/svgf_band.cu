@@ -1,4 +1,7 @@
-// svgf_band.cu — include/svgf_band.h: one frame in horizontal bands, one band per GPU, halos exchanged with NCCL send/recv.
+// svgf_band.cu — include/svgf_band.h: one frame in horizontal bands, one band per GPU.  The frame of a band is a resumable
+// state machine (frame_begin / frame_run / frame_exchange) that stops at every exchange; three transports perform it:
+// NCCL send/recv, peer-memory pulls between processes (CUDA IPC mappings + flag words + one pull kernel per exchange), and
+// peer copies between the bands of an in-process group.
 //
 // What runs where, per frame (N = 5 levels; main = the caller's stream, side = the driver's exchange stream):
 //   main: [wait STATE(t-1)]  temporal + variance (whole local image)  level 0 (whole local image)
@@ -319,10 +322,9 @@ svgf_status ipc_publish_state(svgf_band *b) {
 
 // Peer-memory transport, one exchange (side stream, after the event that says this band's rows are final): READY_HALO for
 // the neighbours, then ONE kernel that waits for theirs, pulls their rows into the aprons and acknowledges.
-svgf_status exchange_ipc(svgf_band *b) {
+svgf_status exchange_ipc(svgf_band *b, bool has_halo, bool with_state) {
     if (b->dry_run) return SVGF_OK;
     svgf_band::Frame &f = b->f;
-    const bool has_halo = f.pc >= 0;
     const int lo = b->band_lo(), hi = b->band_hi();
     if (has_halo) {
         b->halo_seq++;
@@ -351,7 +353,7 @@ svgf_status exchange_ipc(svgf_band *b) {
                 total += bytes;
             }
         }
-        if (f.carries_state) {
+        if (with_state) {
             a.wait[a.nwait++] = FlagRef{p.flags + kFlagReadyState * kFlagStride, b->ticket};
             a.signal[a.nsignal++] = FlagRef{p.flags + (kFlagPulledState + mine_at_peer) * kFlagStride, b->ticket};
             const char *src = p.staging + (size_t)mine_at_peer * b->staging_side_bytes;   // the upper neighbour's BOTTOM rows, the lower one's TOP rows
@@ -378,7 +380,8 @@ extern "C" {
 // The a-trous levels 1..levels-1 of one band's frame as a list of steps (level 0 always covers the whole local image).
 //  * a level below 3 recomputes its halo: it produces the band plus the rows the not-exchanging levels above it still
 //    need (8 rows around the band for level 1 when level 2 follows), rounded out to whole row blocks of 12 * 2^level rows;
-//  * a level >= 3 waits for its halo (2 * 2^level rows of the previous level's output from each neighbour);
+//  * a level >= 3 waits for its halo (2 * 2^level rows of the previous level's output from each neighbour) - before its
+//    first launch, or, when it feeds no exchange itself, after the row blocks that do not read apron rows;
 //  * a level whose successor is >= 3 runs the row blocks holding the rows its neighbours need FIRST, then the exchange
 //    of those rows is posted, then the interior row blocks run.
 int svgf_band_plan(int rank, int world, int band_lo, int band_hi, int local_rows, int levels, svgf_band_step *steps, int max_steps) {
@@ -397,7 +400,24 @@ int svgf_band_plan(int rank, int world, int band_lo, int band_hi, int local_rows
         const int r0 = band_lo - reach > 0 ? band_lo - reach : 0, r1 = band_hi + reach < local_rows ? band_hi + reach : local_rows;
         const int ybA = r0 / B, ybB = (r1 + B - 1) / B;
         const bool feeds_exchange = (l + 1 < levels) && (l + 1 >= first_exchanged) && world > 1;
-        if (l >= first_exchanged && world > 1) push(SVGF_BAND_STEP_WAIT_HALO, l, 0, 0, 2 << l);
+        const bool waits = l >= first_exchanged && world > 1;
+        if (waits && !feeds_exchange) {
+            // a level that only CONSUMES a halo: the row blocks out of the halo's reach run first, under the exchange
+            const int reach_in = 2 << l;
+            int t1 = rank > 0 ? (band_lo + reach_in + B - 1) / B : ybA;       // [ybA, t1) read the top apron
+            int b0 = rank + 1 < world ? (band_hi - reach_in) / B : ybB;       // [b0, ybB) read the bottom apron
+            if (t1 > ybB) t1 = ybB;
+            if (b0 < ybA) b0 = ybA;
+            if (t1 < b0) {
+                push(SVGF_BAND_STEP_LAUNCH, l, t1, b0 - t1, 0);
+                push(SVGF_BAND_STEP_WAIT_HALO, l, 0, 0, reach_in);
+                if (t1 > ybA && ybB > b0) push(SVGF_BAND_STEP_LAUNCH, l, ybA, t1 - ybA, 0, b0, ybB - b0);
+                else if (t1 > ybA) push(SVGF_BAND_STEP_LAUNCH, l, ybA, t1 - ybA, 0);
+                else if (ybB > b0) push(SVGF_BAND_STEP_LAUNCH, l, b0, ybB - b0, 0);
+                continue;
+            }
+        }
+        if (waits) push(SVGF_BAND_STEP_WAIT_HALO, l, 0, 0, 2 << l);
         if (!feeds_exchange) {
             push(SVGF_BAND_STEP_LAUNCH, l, ybA, ybB - ybA, 0);
             continue;
@@ -654,9 +674,14 @@ svgf_status frame_begin(svgf_band *b, const svgf_params *params, const svgf_gbuf
     f.state[0] = Plane{(char *)bufs->render[P], (size_t)b->W * ct};
     f.state[1] = Plane{(char *)bufs->moments[P], (size_t)b->W * mt};
     f.state[2] = Plane{(char *)bufs->history, (size_t)b->W};
-    if (b->ipc && !b->dry_run) {
+    if (b->ipc) {
+        // peer-memory transport: the state rows are published and the neighbours' pulled right away, by a kernel of their own
+        // under levels 1-2 - a separate launch costs nothing here, and the last halo exchange (the exposed one) stays small
         BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, b->ev_l0, 0)));
-        BAND_TRY(ipc_publish_state(b));
+        if (!b->dry_run) BAND_TRY(ipc_publish_state(b));
+        BAND_TRY(exchange_ipc(b, false, true));
+        BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_state, b->side)));
+        b->state_pending = true;
     }
 
     // levels 1..N-1 as planned by svgf_band_plan (the same function the CPU tests check)
@@ -667,7 +692,7 @@ svgf_status frame_begin(svgf_band *b, const svgf_params *params, const svgf_gbuf
         if (f.steps[i].kind == SVGF_BAND_STEP_EXCHANGE) f.last_exchange = i;
     f.src = 0;                                     // lattice colour set holding the input of the current level
     f.cur_level = 1; f.n_halo = 0;
-    f.pc = f.last_exchange < 0 ? -1 : 0;           // -1: the state-only exchange comes first
+    f.pc = (f.last_exchange < 0 && !b->ipc) ? -1 : 0;   // -1: the state-only exchange comes first (NCCL / group transports)
     return SVGF_OK;
 }
 
@@ -703,7 +728,7 @@ svgf_status frame_run(svgf_band *b, bool *stopped) {
             f.lattice[2] = Plane{(char *)dst.lz + pad, row_bytes};
             f.sets[0] = PlaneSet{f.lattice, 3, st.rows};
             f.sets[1] = PlaneSet{f.state, 3, SVGF_BAND_APRON};
-            f.carries_state = (f.pc == f.last_exchange);
+            f.carries_state = (f.pc == f.last_exchange) && !b->ipc;
             f.n_sets = f.carries_state ? 2 : 1;
             f.ready = evb; f.done = b->ev_halo[(st.level + 1 - 3) & 1];
             *stopped = true;
@@ -722,7 +747,7 @@ svgf_status frame_exchange(svgf_band *b) {
             if (nb) BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, nb->f.ready, 0)));
         BAND_TRY(exchange_copy(b));
     } else if (b->ipc) {
-        BAND_TRY(exchange_ipc(b));
+        BAND_TRY(exchange_ipc(b, true, false));
     } else {
         BAND_TRY(exchange(b, f.sets, f.n_sets));
     }

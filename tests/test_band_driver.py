@@ -58,13 +58,25 @@ def test_band_plan_covers_what_each_level_must_produce(world, levels, height):
             need = set(range(max(0, lo - reach), min(rows, hi + reach)))
             mine = [s for s in plan if s[1] == l]
             covered, before_exchange = set(), set()
-            seen_exchange = False
+            seen_exchange = seen_wait = False
+            reads_apron = set()          # rows whose 5-tap column reaches a neighbour's rows
+            if world > 1 and l >= 3:
+                if rank > 0:
+                    reads_apron |= set(range(0, lo + (2 << l)))
+                if rank + 1 < world:
+                    reads_apron |= set(range(hi - (2 << l), rows + B))
             for kind, _, yb0, nyb, r, yb1, nyb1 in mine:
+                if kind == WAIT:
+                    assert not seen_wait
+                    seen_wait = True
+                    assert r == 2 << l
                 if kind == LAUNCH:
                     blk = set(range(yb0 * B, (yb0 + nyb) * B)) | set(range(yb1 * B, (yb1 + nyb1) * B))
                     assert len(blk) == (nyb + nyb1) * B, "the two ranges of a launch overlap"
                     assert not (blk & covered), f"rank {rank} level {l}: row blocks launched twice"
                     covered |= blk
+                    if not seen_wait:
+                        assert not (blk & reads_apron), f"rank {rank} level {l}: apron rows read before the halo has arrived"
                     if not seen_exchange:
                         before_exchange |= blk
                 elif kind == EXCHANGE:
@@ -78,9 +90,7 @@ def test_band_plan_covers_what_each_level_must_produce(world, levels, height):
                     assert halo <= before_exchange, f"rank {rank} level {l}: exchange posted before its rows were produced"
             assert need <= covered, f"rank {rank} level {l}: rows {sorted(need - covered)[:4]}... never produced"
             assert seen_exchange == (world > 1 and l + 1 < levels and l + 1 >= 3)
-            assert (mine[0][0] == WAIT) == (world > 1 and l >= 3)
-            if mine[0][0] == WAIT:
-                assert mine[0][4] == 2 << l
+            assert seen_wait == (world > 1 and l >= 3)
 
 
 def test_band_plan_rejects_what_the_driver_does_not_do():
