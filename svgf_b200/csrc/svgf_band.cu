@@ -80,9 +80,9 @@ struct PullJob { const char *src; char *dst; unsigned long long bytes; };
 struct FlagRef { unsigned *p; unsigned v; };
 struct PullArgs {
     PullJob job[12];
-    FlagRef wait[4], signal[4];
+    FlagRef publish[2], wait[4], signal[4];
     unsigned *counter;
-    int njobs, nwait, nsignal;
+    int njobs, npublish, nwait, nsignal;
 };
 struct FlagArgs { FlagRef wait[4], set[4]; int nwait, nset; };
 
@@ -105,8 +105,13 @@ __device__ void spin_until_reached(const unsigned *p, unsigned v) {
 }
 
 __global__ void __launch_bounds__(256) band_pull_kernel(PullArgs a) {
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
+        // this band's own rows are final (the launch is ordered behind the kernels that wrote them): say so first - every
+        // CTA does, the value is the same, so no CTA's wait can depend on another CTA of this grid having been scheduled
+        if (a.npublish) __threadfence_system();
+        for (int i = 0; i < a.npublish; i++) st_release_sys(a.publish[i].p, a.publish[i].v);
         for (int i = 0; i < a.nwait; i++) spin_until_reached(a.wait[i].p, a.wait[i].v);
+    }
     __syncthreads();
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
     for (int j = 0; j < a.njobs; j++) {
@@ -168,7 +173,7 @@ struct svgf_band {
     int y0 = 0, y1 = 0, ly0 = 0, ly1 = 0;
     NcclComm comm = nullptr;
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_l0 = nullptr, ev_boundary[2] = {nullptr, nullptr}, ev_halo[2] = {nullptr, nullptr}, ev_state = nullptr;
+    cudaEvent_t ev_l0 = nullptr, ev_boundary[2] = {nullptr, nullptr}, ev_halo[2] = {nullptr, nullptr}, ev_state = nullptr, ev_pulled = nullptr;
     bool state_pending = false;
     bool dry_run = false;          // SVGF_FLAG_BAND_NO_EXCHANGE of the current call
     int last_err = 0;
@@ -315,9 +320,7 @@ svgf_status ipc_publish_state(svgf_band *b) {
             dst += bytes;
         }
     }
-    FlagArgs a{};
-    a.set[a.nset++] = FlagRef{b->flags + kFlagReadyState * kFlagStride, b->ticket};
-    return launch_flags(b, a, b->side);
+    return SVGF_OK;          // READY_STATE is published by the pull kernel that follows on the same stream
 }
 
 // Peer-memory transport, one exchange (side stream, after the event that says this band's rows are final): READY_HALO for
@@ -326,14 +329,13 @@ svgf_status exchange_ipc(svgf_band *b, bool has_halo, bool with_state) {
     if (b->dry_run) return SVGF_OK;
     svgf_band::Frame &f = b->f;
     const int lo = b->band_lo(), hi = b->band_hi();
-    if (has_halo) {
-        b->halo_seq++;
-        FlagArgs r{};
-        r.set[r.nset++] = FlagRef{b->flags + kFlagReadyHalo * kFlagStride, b->halo_seq};
-        BAND_TRY(launch_flags(b, r, b->side));
-    }
     PullArgs a{};
     a.counter = b->pull_counter;
+    if (has_halo) {
+        b->halo_seq++;
+        a.publish[a.npublish++] = FlagRef{b->flags + kFlagReadyHalo * kFlagStride, b->halo_seq};
+    }
+    if (with_state) a.publish[a.npublish++] = FlagRef{b->flags + kFlagReadyState * kFlagStride, b->ticket};
     unsigned long long total = 0;
     const size_t pad = has_halo ? (size_t)svgf::kLatPadY * f.lattice[0].row_bytes : 0;
     const int set_base = (1 - f.src) * 3;                  // the lattice colour set this level wrote, here and on the neighbours
@@ -495,7 +497,7 @@ static svgf_status band_create(svgf_band **out, int device, int rank, int world,
         e = cudaDeviceGetStreamPriorityRange(&lowest, &greatest);
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->side, cudaStreamNonBlocking, greatest);
     }
-    cudaEvent_t *evs[] = {&b->ev_l0, &b->ev_boundary[0], &b->ev_boundary[1], &b->ev_halo[0], &b->ev_halo[1], &b->ev_state};
+    cudaEvent_t *evs[] = {&b->ev_l0, &b->ev_boundary[0], &b->ev_boundary[1], &b->ev_halo[0], &b->ev_halo[1], &b->ev_state, &b->ev_pulled};
     for (cudaEvent_t *ev : evs)
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     int nr = 0;
@@ -593,7 +595,7 @@ void svgf_band_destroy(svgf_band *b) {
     if (b->staging) cudaFree(b->staging);
     if (b->flags) cudaFree(b->flags);
     if (b->side) cudaStreamDestroy(b->side);
-    cudaEvent_t evs[] = {b->ev_l0, b->ev_boundary[0], b->ev_boundary[1], b->ev_halo[0], b->ev_halo[1], b->ev_state};
+    cudaEvent_t evs[] = {b->ev_l0, b->ev_boundary[0], b->ev_boundary[1], b->ev_halo[0], b->ev_halo[1], b->ev_state, b->ev_pulled};
     for (cudaEvent_t ev : evs)
         if (ev) cudaEventDestroy(ev);
     svgf_destroy(b->ctx);
@@ -643,7 +645,12 @@ svgf_status frame_begin(svgf_band *b, const svgf_params *params, const svgf_gbuf
     if (b->ipc) {
         if (!b->ipc_connected) return SVGF_INVALID_ARG;
         b->ticket++;
-        if (!b->dry_run) BAND_TRY(ipc_wait_pulled(b, s));
+        if (!b->dry_run) {
+            // off the main stream: the check runs beside the temporal pass; level 0 (the first kernel that overwrites rows a
+            // neighbour reads) and the staging copies (same side stream) are ordered behind it
+            BAND_TRY(ipc_wait_pulled(b, b->side));
+            BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_pulled, b->side)));
+        }
     }
     if (b->in_group) {
         // a neighbour copies rows out of THIS band's planes on its own side stream: this frame must not overwrite them
@@ -665,6 +672,7 @@ svgf_status frame_begin(svgf_band *b, const svgf_params *params, const svgf_gbuf
 
     // level 0 over the whole local image: it also writes the normal planes every later level reads in the apron, and the
     // colour history of the apron rows is replaced by the neighbours' below
+    if (b->ipc && !b->dry_run) BAND_TRY(band_cuda(b, cudaStreamWaitEvent(s, b->ev_pulled, 0)));
     BAND_TRY(svgf::staged_level(c, params, f.slot, 0, 0, bufs->filter[0], 0, nullptr, bufs->render[P], 0, 0, 0, 0, false, s));
     // next frame's previous-frame state - colour history (level 0's output), moments and history lengths - is final from here
     // on.  It travels with the LAST halo exchange of the frame (one NCCL launch fewer; it is not needed before the next
