@@ -9,8 +9,10 @@
 //   side:                                                               `-> exchange 16 rows of level 2's output -> [ev]
 //   main:                       [wait]  level 3: both boundary strips -> [ev]   level 3: interior row blocks
 //   side:                                                                 `-> exchange 32 rows of level 3's output + STATE(t) -> [ev]
-//   main:                                                      [wait]  level 4 (band rows) -> filter[0]
+//   main:       level 4: the row blocks that read no apron row   [wait]  level 4: the others -> filter[0]
 //   frame t+1, main: [wait STATE(t)]
+// (NCCL and the in-process group send STATE(t) with the last halo exchange as drawn; the peer-memory transport pulls it with
+// a kernel of its own right after level 0.)
 // Levels 0..2 do not exchange: their halos (2 + 4 + 8 rows), the variance pass's 7x7 window and the motion vectors' reach are
 // covered by computing those stages up to 17 + max_motion rows into the 32-row apron.  Only lattice planes travel for
 // the per-level exchanges (the level that follows reads them by TMA); whole padded rows, so one contiguous block per plane.
