@@ -27,6 +27,24 @@ def test_band_create_validates_its_partition_before_touching_a_device():
     assert not h.value
 
 
+def test_the_other_transports_validate_before_touching_a_device_too():
+    lib = _lib.lib()
+    h = C.c_void_p()
+    assert lib.svgf_band_create_ipc(C.byref(h), 0, 3, 2, 256, 256, 0, None) == _lib.SVGF_INVALID_ARG          # rank out of range
+    assert lib.svgf_band_create_ipc(C.byref(h), 0, 0, 4, 256, 100, 0, None) == _lib.SVGF_UNSUPPORTED          # bands < the apron
+    assert not h.value
+    blob = (C.c_ubyte * 640)()
+    assert lib.svgf_band_ipc_export(None, blob) == _lib.SVGF_INVALID_ARG
+    assert lib.svgf_band_ipc_connect(None, blob, blob) == _lib.SVGF_INVALID_ARG
+    hs = (C.c_void_p * 2)()
+    dv = (C.c_int32 * 2)(0, 0)
+    assert lib.svgf_band_create_group(hs, dv, 0, 256, 256, 0, None) == _lib.SVGF_INVALID_ARG                  # no bands
+    assert lib.svgf_band_create_group(None, dv, 2, 256, 256, 0, None) == _lib.SVGF_INVALID_ARG
+    assert lib.svgf_band_create_group(hs, dv, 2, 256, 40, 0, None) == _lib.SVGF_UNSUPPORTED                   # 20-row bands
+    assert not hs[0] and not hs[1]
+    assert lib.svgf_band_group_frame(None, 2, None, None, None, None) == _lib.SVGF_INVALID_ARG
+
+
 def _plan(rank, world, lo, hi, rows, levels):
     steps = (_lib.SvgfBandStep * 32)()
     n = _lib.lib().svgf_band_plan(rank, world, lo, hi, rows, levels, steps, 32)
