@@ -82,11 +82,11 @@ struct PullJob { const char *src; char *dst; unsigned long long bytes; };
 struct FlagRef { unsigned *p; unsigned v; };
 struct PullArgs {
     PullJob job[12];
-    FlagRef publish[2], wait[4], signal[4];
+    FlagRef signal[4];
     unsigned *counter;
-    int njobs, npublish, nwait, nsignal;
+    int njobs, nsignal;
 };
-struct FlagArgs { FlagRef wait[4], set[4]; int nwait, nset; };
+struct FlagArgs { FlagRef publish[2], wait[4]; int npublish, nwait; };
 
 constexpr long long kSpinLimitClocks = 20000000000LL;      // ~10 s: a neighbour that never arrives becomes a CUDA error, not a hang
 
@@ -106,15 +106,10 @@ __device__ void spin_until_reached(const unsigned *p, unsigned v) {
     }
 }
 
+// The copy of one exchange.  It is launched behind band_flag_kernel, which has done the waiting with ONE thread: a grid that
+// spins occupies the SM slots the level kernels on the main stream need (64 waiting CTAs cost the interior of a level a
+// fifth of the GPU for as long as a neighbour lags - measured at N = 4: 1.10 ms against 0.97 ms).
 __global__ void __launch_bounds__(256) band_pull_kernel(PullArgs a) {
-    if (threadIdx.x == 0) {
-        // this band's own rows are final (the launch is ordered behind the kernels that wrote them): say so first - every
-        // CTA does, the value is the same, so no CTA's wait can depend on another CTA of this grid having been scheduled
-        if (a.npublish) __threadfence_system();
-        for (int i = 0; i < a.npublish; i++) st_release_sys(a.publish[i].p, a.publish[i].v);
-        for (int i = 0; i < a.nwait; i++) spin_until_reached(a.wait[i].p, a.wait[i].v);
-    }
-    __syncthreads();
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
     for (int j = 0; j < a.njobs; j++) {
         const PullJob q = a.job[j];
@@ -143,10 +138,12 @@ __global__ void __launch_bounds__(256) band_pull_kernel(PullArgs a) {
     }
 }
 
+// One thread: publish this band's READY numbers (the launch is ordered behind the kernels that wrote the rows), then wait for
+// the neighbours' numbers (READY before a pull, PULLED at the start of a frame).
 __global__ void band_flag_kernel(FlagArgs a) {
+    if (a.npublish) __threadfence_system();
+    for (int i = 0; i < a.npublish; i++) st_release_sys(a.publish[i].p, a.publish[i].v);
     for (int i = 0; i < a.nwait; i++) spin_until_reached(a.wait[i].p, a.wait[i].v);
-    __threadfence_system();
-    for (int i = 0; i < a.nset; i++) st_release_sys(a.set[i].p, a.set[i].v);
 }
 
 struct IpcBlob {                       // what svgf_band_ipc_export hands to the neighbours (SVGF_BAND_IPC_BYTES)
@@ -296,8 +293,8 @@ svgf_status launch_flags(svgf_band *b, const FlagArgs &a, cudaStream_t s) {
     return band_cuda(b, cudaGetLastError());
 }
 
-// Peer-memory transport, frame begin (main stream): the rows this frame is about to overwrite - boundary rows of the lattice
-// planes, the state staging block - must have been fetched by the neighbours (they were, long ago, unless a rank lags).
+// Peer-memory transport, frame begin: the rows this frame is about to overwrite - boundary rows of the lattice planes, the
+// state staging block - must have been fetched by the neighbours (they were, long ago, unless a rank lags).
 svgf_status ipc_wait_pulled(svgf_band *b, cudaStream_t s) {
     FlagArgs a{};
     for (int d = 0; d < 2; d++) {
@@ -322,22 +319,24 @@ svgf_status ipc_publish_state(svgf_band *b) {
             dst += bytes;
         }
     }
-    return SVGF_OK;          // READY_STATE is published by the pull kernel that follows on the same stream
+    return SVGF_OK;          // READY_STATE is published by the flag kernel of the pull that follows on the same stream
 }
 
-// Peer-memory transport, one exchange (side stream, after the event that says this band's rows are final): READY_HALO for
-// the neighbours, then ONE kernel that waits for theirs, pulls their rows into the aprons and acknowledges.
+// Peer-memory transport, one exchange (side stream, after the event that says this band's rows are final): a one-thread
+// kernel publishes READY for the neighbours and waits for theirs, then one grid pulls their rows into the aprons and
+// acknowledges.
 svgf_status exchange_ipc(svgf_band *b, bool has_halo, bool with_state) {
     if (b->dry_run) return SVGF_OK;
     svgf_band::Frame &f = b->f;
     const int lo = b->band_lo(), hi = b->band_hi();
     PullArgs a{};
+    FlagArgs w{};
     a.counter = b->pull_counter;
     if (has_halo) {
         b->halo_seq++;
-        a.publish[a.npublish++] = FlagRef{b->flags + kFlagReadyHalo * kFlagStride, b->halo_seq};
+        w.publish[w.npublish++] = FlagRef{b->flags + kFlagReadyHalo * kFlagStride, b->halo_seq};
     }
-    if (with_state) a.publish[a.npublish++] = FlagRef{b->flags + kFlagReadyState * kFlagStride, b->ticket};
+    if (with_state) w.publish[w.npublish++] = FlagRef{b->flags + kFlagReadyState * kFlagStride, b->ticket};
     unsigned long long total = 0;
     const size_t pad = has_halo ? (size_t)svgf::kLatPadY * f.lattice[0].row_bytes : 0;
     const int set_base = (1 - f.src) * 3;                  // the lattice colour set this level wrote, here and on the neighbours
@@ -347,7 +346,7 @@ svgf_status exchange_ipc(svgf_band *b, bool has_halo, bool with_state) {
         const int mine_at_peer = 1 - d;                    // the upper neighbour knows this band as its `down`
         if (has_halo) {
             const int rows = f.sets[0].rows;
-            a.wait[a.nwait++] = FlagRef{p.flags + kFlagReadyHalo * kFlagStride, b->halo_seq};
+            w.wait[w.nwait++] = FlagRef{p.flags + kFlagReadyHalo * kFlagStride, b->halo_seq};
             a.signal[a.nsignal++] = FlagRef{p.flags + (kFlagPulledHalo + mine_at_peer) * kFlagStride, b->halo_seq};
             for (int k = 0; k < 3; k++) {
                 const size_t rb = f.lattice[k].row_bytes, bytes = (size_t)rows * rb;
@@ -358,7 +357,7 @@ svgf_status exchange_ipc(svgf_band *b, bool has_halo, bool with_state) {
             }
         }
         if (with_state) {
-            a.wait[a.nwait++] = FlagRef{p.flags + kFlagReadyState * kFlagStride, b->ticket};
+            w.wait[w.nwait++] = FlagRef{p.flags + kFlagReadyState * kFlagStride, b->ticket};
             a.signal[a.nsignal++] = FlagRef{p.flags + (kFlagPulledState + mine_at_peer) * kFlagStride, b->ticket};
             const char *src = p.staging + (size_t)mine_at_peer * b->staging_side_bytes;   // the upper neighbour's BOTTOM rows, the lower one's TOP rows
             for (int k = 0; k < 3; k++) {
@@ -370,6 +369,7 @@ svgf_status exchange_ipc(svgf_band *b, bool has_halo, bool with_state) {
             }
         }
     }
+    BAND_TRY(launch_flags(b, w, b->side));
     int grid = (int)(total / (256ull * 16 * 8)) + 1;
     if (grid > 64) grid = 64;
     band_pull_kernel<<<grid, 256, 0, b->side>>>(a);
@@ -804,6 +804,18 @@ svgf_status svgf_band_create_group(svgf_band **out, const int32_t *devices, int 
         out[g]->up = g > 0 ? out[g - 1] : nullptr;
         out[g]->down = g + 1 < world ? out[g + 1] : nullptr;
     }
+    // neighbours on different devices: direct peer copies where the hardware allows (otherwise the runtime stages them)
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (int g = 0; g + 1 < world; g++) {
+        const int a = devices[g], b = devices[g + 1];
+        if (a == b) continue;
+        int ok = 0;
+        if (cudaDeviceCanAccessPeer(&ok, a, b) == cudaSuccess && ok && cudaSetDevice(a) == cudaSuccess) cudaDeviceEnablePeerAccess(b, 0);
+        if (cudaDeviceCanAccessPeer(&ok, b, a) == cudaSuccess && ok && cudaSetDevice(b) == cudaSuccess) cudaDeviceEnablePeerAccess(a, 0);
+        cudaGetLastError();                    // already enabled is fine
+    }
+    if (prev >= 0) cudaSetDevice(prev);
     return SVGF_OK;
 }
 
