@@ -172,6 +172,7 @@ struct svgf_band {
     int y0 = 0, y1 = 0, ly0 = 0, ly1 = 0;
     NcclComm comm = nullptr;
     cudaStream_t side = nullptr;
+    cudaStream_t side_state = nullptr; // peer-memory transport: the state rows travel on a stream of their own
     cudaEvent_t ev_l0 = nullptr, ev_boundary[2] = {nullptr, nullptr}, ev_halo[2] = {nullptr, nullptr}, ev_state = nullptr, ev_pulled = nullptr;
     bool state_pending = false;
     bool dry_run = false;          // SVGF_FLAG_BAND_NO_EXCHANGE of the current call
@@ -184,7 +185,7 @@ struct svgf_band {
     IpcPeer peer[2];                   // 0 = up (rank - 1), 1 = down (rank + 1)
     char *staging = nullptr;           // [side 0 = my top band rows, 1 = bottom][colour, moments, history] of the last frame
     size_t staging_side_bytes = 0;
-    unsigned *flags = nullptr, *pull_counter = nullptr;
+    unsigned *flags = nullptr, *pull_counter = nullptr, *pull_counter_state = nullptr;
     unsigned ticket = 0, halo_seq = 0; // frames begun / halo exchanges posted (the same on every rank)
     uint64_t extra_launches = 0;       // flag and pull kernels (svgf_band_launch_count)
 
@@ -315,7 +316,7 @@ svgf_status ipc_publish_state(svgf_band *b) {
         const int row0 = d == 0 ? lo : hi - SVGF_BAND_APRON;
         for (int k = 0; k < 3; k++) {
             const size_t bytes = (size_t)SVGF_BAND_APRON * f.state[k].row_bytes;
-            BAND_TRY(band_cuda(b, cudaMemcpyAsync(dst, f.state[k].base + (size_t)row0 * f.state[k].row_bytes, bytes, cudaMemcpyDeviceToDevice, b->side)));
+            BAND_TRY(band_cuda(b, cudaMemcpyAsync(dst, f.state[k].base + (size_t)row0 * f.state[k].row_bytes, bytes, cudaMemcpyDeviceToDevice, b->side_state)));
             dst += bytes;
         }
     }
@@ -328,10 +329,11 @@ svgf_status ipc_publish_state(svgf_band *b) {
 svgf_status exchange_ipc(svgf_band *b, bool has_halo, bool with_state) {
     if (b->dry_run) return SVGF_OK;
     svgf_band::Frame &f = b->f;
+    cudaStream_t stream = with_state ? b->side_state : b->side;     // a call moves the halos or the state, never both
     const int lo = b->band_lo(), hi = b->band_hi();
     PullArgs a{};
     FlagArgs w{};
-    a.counter = b->pull_counter;
+    a.counter = with_state ? b->pull_counter_state : b->pull_counter;
     if (has_halo) {
         b->halo_seq++;
         w.publish[w.npublish++] = FlagRef{b->flags + kFlagReadyHalo * kFlagStride, b->halo_seq};
@@ -369,10 +371,10 @@ svgf_status exchange_ipc(svgf_band *b, bool has_halo, bool with_state) {
             }
         }
     }
-    BAND_TRY(launch_flags(b, w, b->side));
+    BAND_TRY(launch_flags(b, w, stream));
     int grid = (int)(total / (256ull * 16 * 8)) + 1;
     if (grid > 64) grid = 64;
-    band_pull_kernel<<<grid, 256, 0, b->side>>>(a);
+    band_pull_kernel<<<grid, 256, 0, stream>>>(a);
     b->extra_launches++;
     return band_cuda(b, cudaGetLastError());
 }
@@ -508,9 +510,15 @@ static svgf_status band_create(svgf_band **out, int device, int rank, int world,
         const size_t ct = storage == SVGF_STORE_F32 ? 16 : 8, mt = storage == SVGF_STORE_F32 ? 8 : 4;
         b->staging_side_bytes = ((size_t)SVGF_BAND_APRON * width * (ct + mt + 1) + 255) & ~(size_t)255;
         e = cudaMalloc(&b->staging, 2 * b->staging_side_bytes);
-        if (e == cudaSuccess) e = cudaMalloc(&b->flags, (kFlagWords * kFlagStride + 1) * sizeof(unsigned));
-        if (e == cudaSuccess) e = cudaMemset(b->flags, 0, (kFlagWords * kFlagStride + 1) * sizeof(unsigned));
-        if (e == cudaSuccess) b->pull_counter = b->flags + kFlagWords * kFlagStride;
+        if (e == cudaSuccess) e = cudaMalloc(&b->flags, (kFlagWords + 2) * kFlagStride * sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMemset(b->flags, 0, (kFlagWords + 2) * kFlagStride * sizeof(unsigned));
+        if (e == cudaSuccess) {
+            b->pull_counter = b->flags + kFlagWords * kFlagStride;
+            b->pull_counter_state = b->flags + (kFlagWords + 1) * kFlagStride;
+            int lowest = 0, greatest = 0;
+            e = cudaDeviceGetStreamPriorityRange(&lowest, &greatest);
+            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b->side_state, cudaStreamNonBlocking, greatest);
+        }
         if (e == cudaSuccess && svgf::lattice_prepare(b->ctx, nullptr) != SVGF_OK) e = cudaErrorMemoryAllocation;
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
     }
@@ -585,6 +593,7 @@ void svgf_band_destroy(svgf_band *b) {
     cudaGetDevice(&prev);
     cudaSetDevice(b->device);
     if (b->side) cudaStreamSynchronize(b->side);
+    if (b->side_state) { cudaStreamSynchronize(b->side_state); cudaStreamDestroy(b->side_state); }
     if (b->up) { cudaStreamSynchronize(b->up->side); b->up->down = nullptr; }       // a neighbour's copies read this band's planes
     if (b->down) { cudaStreamSynchronize(b->down->side); b->down->up = nullptr; }
     if (b->comm) nccl().CommDestroy(b->comm);
@@ -687,10 +696,14 @@ svgf_status frame_begin(svgf_band *b, const svgf_params *params, const svgf_gbuf
     if (b->ipc) {
         // peer-memory transport: the state rows are published and the neighbours' pulled right away, by a kernel of their own
         // under levels 1-2 - a separate launch costs nothing here, and the last halo exchange (the exposed one) stays small
-        BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side, b->ev_l0, 0)));
-        if (!b->dry_run) BAND_TRY(ipc_publish_state(b));
+        // on a stream of their own: a neighbour whose level 0 ends later must not hold up this band's halo exchanges
+        BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side_state, b->ev_l0, 0)));
+        if (!b->dry_run) {
+            BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side_state, b->ev_pulled, 0)));   // the staging block has been fetched
+            BAND_TRY(ipc_publish_state(b));
+        }
         BAND_TRY(exchange_ipc(b, false, true));
-        BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_state, b->side)));
+        BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_state, b->side_state)));
         b->state_pending = true;
     }
 
