@@ -376,10 +376,17 @@ def run_streams_1080p(args, rank, world, local):
             "ms_total": round(ms_max, 3), "streams_per_gpu": len(mine), "gpu_launches": int(launches), "scaling": "strong (64 streams in total)"}
 
 
+def band_transport(args, world):
+    """Measured on B200 (8K frame): N=2 1.739 / 1.752 ms (peer memory / NCCL), N=4 1.09 / 0.97, N=8 0.675 / 0.713."""
+    if args.band_transport != "auto":
+        return args.band_transport
+    return "ipc" if world >= 8 else "nccl"
+
+
 def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames, transport=None, fixed_bounds=None):
     """K timed 8K frames in `world` bands through the native band driver + a bit-identity check on rank 0.
     transport: "ipc" (peer-memory pulls over NVLink) or "nccl" (send/recv); fixed_bounds: skip the balancing passes."""
-    transport = transport or args.band_transport
+    transport = transport or band_transport(args, world)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -675,7 +682,7 @@ def run_ours(args, rank, world, local):
             bw, bh = WORKLOADS["8k"]
             bands_rec = run_band_frames(args, rank, world, local, bw, bh, K=args.band_frames, Wm=4, check_frames=3)
             # the same frames, same band heights, over the other transport (timing only)
-            other = "nccl" if args.band_transport == "ipc" else "ipc"
+            other = "nccl" if band_transport(args, world) == "ipc" else "ipc"
             bands_other = run_band_frames(args, rank, world, local, bw, bh, K=args.band_frames, Wm=4, check_frames=1, transport=other,
                                           fixed_bounds=bands_rec["band_bounds"])
 
@@ -916,7 +923,8 @@ def main():
     ap.add_argument("--prefilter", type=int, default=0, help="svgf_params.variance_prefilter (1 = 3x3 Gaussian, not in the reference)")
     ap.add_argument("--reproj", type=int, default=0, help="svgf_params.reproj_mode (1 = bilinear 2x2, not in the reference)")
     ap.add_argument("--flags", type=int, default=0, help="svgf_params.flags for A/B runs (8 = no uniform-normal tile shortcut, 32 = no staged levels)")
-    ap.add_argument("--band-transport", default="ipc", choices=["ipc", "nccl"], help="bands: halo transport of the native driver")
+    ap.add_argument("--band-transport", default="auto", choices=["auto", "ipc", "nccl"],
+                    help="bands: halo transport of the native driver (auto: peer memory from 8 ranks on, NCCL below - what measured faster)")
     ap.add_argument("--band-balance", type=int, default=2, help="bands: 0 = equal heights, 1 = heights balanced by the background share of the first frame, 2 = 1 + two measured calibration passes")
     ap.add_argument("--band-bg-cost", type=float, default=0.45, help="bands: cost of a background pixel relative to a filtered one")
     ap.add_argument("--mode", default="streams", choices=["streams", "bands"],
