@@ -536,7 +536,7 @@ def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames, transpo
     frame_bytes = (bpp["temporal"] + bpp["variance"] + bpp["atrous_level"] * args.levels + (bpp["atrous_hist"] if args.levels else 0)) * W * H
     peak, _ = measured_peaks()
     return {"workload": f"BASELINE configs[3]: {W}x{H} frames in {world} horizontal band(s), native band driver (include/svgf_band.h): "
-                        + ("peer-memory transport (CUDA IPC mappings, flag words, one pull kernel per exchange over NVLink)" if transport == "ipc" else "NCCL send/recv")
+                        + ("peer-memory transport (CUDA IPC mappings, flag words, a one-thread wait and one pull grid per exchange over NVLink)" if transport == "ipc" else "NCCL send/recv")
                         + " of 16 + 32 halo rows before levels 3 and 4, boundary row blocks first, state exchange under levels 1-4",
             "transport": transport,
             "value": round(value, 4), "unit": "Gpix/s", "ms_per_step": round(ms_max / K, 5), "steps": K, "warmup": Wm, "scaling": "strong",

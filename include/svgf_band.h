@@ -73,11 +73,12 @@ svgf_status svgf_band_group_frame(svgf_band *const *bands, int world, const svgf
 /* One process per GPU WITHOUT NCCL: the peer-memory transport.  Every rank exports its exchange planes and a few flag words
  * as CUDA IPC handles (svgf_band_ipc_export: SVGF_BAND_IPC_BYTES opaque bytes, to be handed to the two neighbouring ranks by
  * any means - torch.distributed.all_gather_object, MPI, a file) and maps its neighbours' (svgf_band_ipc_connect: the blob of
- * rank - 1 and of rank + 1, NULL where there is none).  svgf_band_frame then exchanges with ONE kernel per exchange on the
- * side stream: it waits for the neighbours' "rows ready" flags, pulls their rows over NVLink (peer loads) into the local
- * aprons and acknowledges, so that a producer never overwrites rows a slower neighbour has not fetched.  Same plan, same
- * kernels and bit-identical results as the NCCL transport; no SM-resident proxy, no host involvement per exchange.  A
- * neighbour that never arrives turns into a CUDA error after ~10 s (the wait traps), not a hang. */
+ * rank - 1 and of rank + 1, NULL where there is none).  svgf_band_frame then exchanges with two launches per exchange on
+ * the side stream: a one-thread kernel publishes this band's "rows ready" number and waits for the neighbours', a grid pulls
+ * their rows over NVLink (peer loads) into the local aprons and acknowledges, so that a producer never overwrites rows a
+ * slower neighbour has not fetched.  Same plan, same kernels and bit-identical results as the NCCL transport; no SM-resident
+ * proxy, no host involvement per exchange.  A neighbour that never arrives turns into a CUDA error after ~10 s (the wait
+ * traps), not a hang. */
 #define SVGF_BAND_IPC_BYTES 640
 svgf_status svgf_band_create_ipc(svgf_band **out, int device, int rank, int world, int width, int full_height, svgf_storage storage,
                                  const int32_t *row_bounds);

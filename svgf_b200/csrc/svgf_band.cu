@@ -75,9 +75,10 @@ struct PlaneSet { const Plane *planes; int n; int rows; };
 
 // ---- the peer-memory transport (svgf_band_create_ipc): flags and pulls over NVLink, no NCCL ---------------------------------
 // Every rank exports its lattice colour planes, a staging block for the state rows and a few flag words (cudaIpc handles);
-// a neighbour maps them.  An exchange is ONE kernel on the consumer's side stream: wait for the producers' READY flags,
-// copy their rows over NVLink into the local aprons, tell them the rows have been read (PULLED flags, so that a producer
-// never overwrites rows a slower neighbour has not fetched yet).  Flags are monotonically increasing sequence numbers.
+// a neighbour maps them.  An exchange, on the consumer's side stream: publish READY and wait for the producers' READY flags
+// (one thread), copy their rows over NVLink into the local aprons (one grid), tell them the rows have been read (PULLED
+// flags, so that a producer never overwrites rows a slower neighbour has not fetched yet).  Flags are monotonically
+// increasing sequence numbers.
 struct PullJob { const char *src; char *dst; unsigned long long bytes; };
 struct FlagRef { unsigned *p; unsigned v; };
 struct PullArgs {
