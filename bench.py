@@ -377,7 +377,7 @@ def run_streams_1080p(args, rank, world, local):
 
 
 def band_transport(args, world):
-    """Measured on B200 (8K frame): N=2 1.739 / 1.752 ms (peer memory / NCCL), N=4 1.09 / 0.97, N=8 0.675 / 0.713."""
+    """Measured on B200 (8K frame): N=2 1.739 / 1.752 ms (peer memory / NCCL), N=4 0.961 / 0.973, N=8 0.675 / 0.712."""
     if args.band_transport != "auto":
         return args.band_transport
     return "ipc" if world >= 8 else "nccl"
@@ -461,6 +461,7 @@ def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames, transpo
         whole.SpatialFilterSteps = args.levels
         whole.Reset()
     bad = 0
+    own_fb = list(bd.Framebuffer)         # Reset() zeroes the driver's G-buffer members: they must never alias ring frames then
     bd.Reset()
     ranges = [None] * world
     if world > 1:
@@ -501,6 +502,10 @@ def run_band_frames(args, rank, world, local, W, H, K, Wm, check_frames, transpo
     torch.cuda.synchronize()
     # ---- timing: a fresh sequence, inputs consumed in place from the resident ring ----
     stream = torch.cuda.current_stream(dev)
+    # (round 2, found at N = 4: the check loop above leaves ring frames in bd.Framebuffer, and Reset() then zeroed the G-buffers
+    # of warm-up frames 1 and 2 - the history restarted at frame 3 and the first timed frames ran the 7x7 variance estimate on
+    # every pixel: +0.12 ms per frame over 24 frames for whichever transport was measured first)
+    bd.Framebuffer = own_fb
     bd.Reset()
     bd.params.flags = args.flags          # e.g. 512 = SVGF_FLAG_BAND_NO_EXCHANGE (diagnostics: compute only)
     keep = bd.RenderBuffer
@@ -680,10 +685,10 @@ def run_ours(args, rank, world, local):
         torch.cuda.empty_cache()
         if world > 1:
             bw, bh = WORKLOADS["8k"]
-            bands_rec = run_band_frames(args, rank, world, local, bw, bh, K=args.band_frames, Wm=4, check_frames=3)
+            bands_rec = run_band_frames(args, rank, world, local, bw, bh, K=args.band_frames, Wm=6, check_frames=3)
             # the same frames, same band heights, over the other transport (timing only)
             other = "nccl" if band_transport(args, world) == "ipc" else "ipc"
-            bands_other = run_band_frames(args, rank, world, local, bw, bh, K=args.band_frames, Wm=4, check_frames=1, transport=other,
+            bands_other = run_band_frames(args, rank, world, local, bw, bh, K=args.band_frames, Wm=6, check_frames=1, transport=other,
                                           fixed_bounds=bands_rec["band_bounds"])
 
     if rank != 0:
@@ -923,8 +928,8 @@ def main():
     ap.add_argument("--prefilter", type=int, default=0, help="svgf_params.variance_prefilter (1 = 3x3 Gaussian, not in the reference)")
     ap.add_argument("--reproj", type=int, default=0, help="svgf_params.reproj_mode (1 = bilinear 2x2, not in the reference)")
     ap.add_argument("--flags", type=int, default=0, help="svgf_params.flags for A/B runs (8 = no uniform-normal tile shortcut, 32 = no staged levels)")
-    ap.add_argument("--band-transport", default="auto", choices=["auto", "ipc", "nccl"],
-                    help="bands: halo transport of the native driver (auto: peer memory from 8 ranks on, NCCL below - what measured faster)")
+    ap.add_argument("--band-transport", default="ipc", choices=["auto", "ipc", "nccl"],
+                    help="bands: halo transport of the native driver (ipc = peer memory; auto: peer memory from 8 ranks on, NCCL below)")
     ap.add_argument("--band-balance", type=int, default=2, help="bands: 0 = equal heights, 1 = heights balanced by the background share of the first frame, 2 = 1 + two measured calibration passes")
     ap.add_argument("--band-bg-cost", type=float, default=0.45, help="bands: cost of a background pixel relative to a filtered one")
     ap.add_argument("--mode", default="streams", choices=["streams", "bands"],

@@ -11,6 +11,6 @@ import json
 d=json.loads(open('$out/${tag}_bench_n4.json').read().splitlines()[-1])
 print('n4', d['value'], d['ms_per_step'], 'e2e', d['e2e'].get('value'))
 print('bands', {k:v for k,v in (d.get('bands') or {}).items() if k not in ('workload',)})
-print('bands_nccl', d.get('bands_nccl'))
+print("other", {k:v for k,v in d.items() if k.startswith("bands_")})
 print('streams', (d.get('streams_1080p') or {}).get('value'))
 " || tail -20 $out/${tag}_bench_n4.err
