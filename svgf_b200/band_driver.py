@@ -109,6 +109,8 @@ class BandDriver:
         return slice(self.ly0, self.ly1)
 
     def Reset(self):
+        """svgf_band_reset + zeroed G-buffer / filter members (whatever they refer to at the time of the call: see
+        SvgfFilter.Reset - a harness that aliases them to its input ring must restore them before resetting)."""
         b = self._bufs()
         self._check(self.lib.svgf_band_reset(self._h, C.byref(b), self._stream()), "svgf_band_reset")
         for g in self.Framebuffer:

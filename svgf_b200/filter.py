@@ -185,7 +185,9 @@ class SvgfFilter:
 
     # -- the reference's stage methods ----------------------------------------------------------------------
     def Reset(self):
-        """First-frame state (undefined in the reference; D12): zero history/colour/moments, all reprojection fails."""
+        """First-frame state (undefined in the reference; D12): zero history/colour/moments, all reprojection fails.
+        Also zeroes whatever ``Framebuffer[0..1]`` and ``FilterBuffer[0..1]`` refer to AT THE TIME OF THE CALL: a caller that
+        has pointed them at its own input planes (zero-copy stepping) must point them back first, or lose those inputs."""
         b = self._bufs()
         self._check(self.lib.svgf_reset(self._ctx, C.byref(b), self._stream()), "svgf_reset")
         for g in self.Framebuffer:
