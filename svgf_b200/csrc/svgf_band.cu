@@ -188,6 +188,7 @@ struct svgf_band {
     size_t staging_side_bytes = 0;
     unsigned *flags = nullptr, *pull_counter = nullptr, *pull_counter_state = nullptr;
     unsigned ticket = 0, halo_seq = 0; // frames begun / halo exchanges posted (the same on every rank)
+    unsigned state_ticket = 0;         // ticket of the last frame whose state rows were published (frames without exchange skip it)
     uint64_t extra_launches = 0;       // flag and pull kernels (svgf_band_launch_count)
 
     // ---- the frame in flight: svgf_band_frame / svgf_band_group_frame advance it from exchange to exchange ----
@@ -302,7 +303,7 @@ svgf_status ipc_wait_pulled(svgf_band *b, cudaStream_t s) {
     for (int d = 0; d < 2; d++) {
         if (!b->peer[d].open) continue;
         a.wait[a.nwait++] = FlagRef{b->flags + (kFlagPulledHalo + d) * kFlagStride, b->halo_seq};
-        a.wait[a.nwait++] = FlagRef{b->flags + (kFlagPulledState + d) * kFlagStride, b->ticket - 1};
+        a.wait[a.nwait++] = FlagRef{b->flags + (kFlagPulledState + d) * kFlagStride, b->state_ticket};
     }
     return launch_flags(b, a, s);
 }
@@ -702,6 +703,7 @@ svgf_status frame_begin(svgf_band *b, const svgf_params *params, const svgf_gbuf
         if (!b->dry_run) {
             BAND_TRY(band_cuda(b, cudaStreamWaitEvent(b->side_state, b->ev_pulled, 0)));   // the staging block has been fetched
             BAND_TRY(ipc_publish_state(b));
+            b->state_ticket = b->ticket;
         }
         BAND_TRY(exchange_ipc(b, false, true));
         BAND_TRY(band_cuda(b, cudaEventRecord(b->ev_state, b->side_state)));
